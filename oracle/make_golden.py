@@ -1,0 +1,280 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (build container only).
+
+    python oracle/make_golden.py            # needs /root/reference; writes tests/golden/
+
+The reference has no tests or golden vectors, so these fixtures -- outputs of
+``/root/reference``'s own modules on seeded inputs -- are what pins the oracle.  The script also
+asserts, while it runs, that the oracle restatement reproduces the reference bit-for-bit on CPU
+(same torch ops in the same order), so a drift in either is caught at generation time.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("USTRUN_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import ssl_step_ref as S  # noqa: E402
+from oracle import unet_ref as U  # noqa: E402
+
+from networks import unet as ref_unet_b  # noqa: E402  (reference)
+from networks import unet_model as ref_unet_a  # noqa: E402
+from networks.dsbn import DomainSpecificBatchNorm2d  # noqa: E402
+from utils import losses as ref_losses  # noqa: E402
+from utils import ramps as ref_ramps  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+SEED = 1337
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def digest(state):
+    """Small per-tensor fingerprint: (sum, abs-sum, first 4 values)."""
+    out = {}
+    for k, v in state.items():
+        v = v.detach().double().flatten()
+        out[k] = np.concatenate([[v.sum().item(), v.abs().sum().item()], np_(v[:4])]).astype(np.float64)
+    return out
+
+
+def assert_same_state(ref_mod, st):
+    sd = ref_mod.state_dict()
+    assert list(sd.keys()) == list(st.keys()), "state_dict keys/order differ"
+    for k in sd:
+        assert torch.equal(sd[k], st[k]), k
+
+
+def run_model_case(name, ref_mod, st, fwd, x, n_classes, extra=None):
+    """Train-mode forward + masked loss backward on the reference module and on the oracle."""
+    g = torch.Generator().manual_seed(SEED + 7)
+    tgt = torch.randint(0, n_classes, (x.shape[0],) + x.shape[2:], generator=g)
+    msk = (torch.rand(x.shape[0], 1, *x.shape[2:], generator=g) > 0.3).float()
+    ref_mod.train()
+    ref_logits = ref_mod(x) if extra is None else ref_mod(x, **extra)
+    dice = ref_losses.DiceLossWithMask(n_classes)
+    ce = torch.nn.CrossEntropyLoss(reduction="none")
+    ref_loss = (ce(ref_logits, tgt) * msk.squeeze(1)).mean() + dice(ref_logits, tgt.unsqueeze(1), mask=msk, softmax=True)
+    ref_loss.backward()
+    ref_grads = {k: p.grad for k, p in ref_mod.named_parameters()}
+
+    params, _ = U.split_state(st)
+    for p in params.values():
+        p.requires_grad_(True)
+    logits = fwd(st, x)
+    loss = S.masked_term(logits, tgt, msk, n_classes, "softmax")
+    loss.backward()
+    assert torch.equal(logits, ref_logits), f"{name}: oracle logits != reference"
+    assert torch.equal(loss, ref_loss), f"{name}: oracle loss != reference"
+    for k, p in params.items():
+        if ref_grads[k] is None:
+            assert p.grad is None, k
+        else:
+            assert torch.allclose(p.grad, ref_grads[k], rtol=0, atol=0), f"{name}: grad {k}"
+    assert_same_state(ref_mod, {k: v.detach() for k, v in st.items()})
+    fx = {"x": np_(x), "target": np_(tgt), "mask": np_(msk), "logits": np_(ref_logits),
+          "loss": np_(ref_loss)}
+    for k, v in digest({k: v for k, v in ref_mod.state_dict().items()}).items():
+        fx["state_after/" + k] = v
+    for k, v in ref_grads.items():
+        if v is not None:
+            fx["grad/" + k] = np.concatenate([[v.double().norm().item(), v.double().sum().item()], np_(v.flatten()[:6]).astype(np.float64)])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+    print(f"{name}: loss={ref_loss.item():.6f}  ok")
+
+
+def case_unet_a(n_channels, n_classes, hw, batch):
+    torch.manual_seed(SEED)
+    ref = ref_unet_a.UNet(n_channels=n_channels, n_classes=n_classes)
+    st = U.init_unet_a(n_channels, n_classes, seed=SEED)
+    assert_same_state(ref, st)
+    x = torch.rand(batch, n_channels, hw, hw, generator=torch.Generator().manual_seed(SEED + 1)) * 2 - 1
+    run_model_case(f"unet_a_c{n_channels}_k{n_classes}_{hw}", ref, st, lambda s, t: U.unet_a_forward(s, t, True), x, n_classes)
+
+
+def case_unet_b(n_channels, n_classes, hw, batch):
+    torch.manual_seed(SEED)
+    ref = ref_unet_b.UNet(n_channels=n_channels, n_classes=n_classes)
+    st = U.init_unet_b(n_channels, n_classes, seed=SEED)
+    assert_same_state(ref, st)
+    x = torch.rand(batch, n_channels, hw, hw, generator=torch.Generator().manual_seed(SEED + 2)) * 2 - 1
+    run_model_case(f"unet_b_c{n_channels}_k{n_classes}_{hw}", ref, st, lambda s, t: U.unet_b_forward(s, t, True), x, n_classes)
+
+
+class _EncRec(torch.nn.Module):
+    """The only DSBN network constructible upstream: Encoder(bn) + Rec_Decoder(dsbn)."""
+
+    def __init__(self, c, classes, domains):
+        super().__init__()
+        self.enc = ref_unet_b.Encoder(c=c, norm="bn")
+        self.dec = ref_unet_b.Rec_Decoder(num_classes=classes, norm="dsbn", num_domains=domains)
+
+    def forward(self, x, domain_label=None):
+        return self.dec(self.enc(x)[-1], domain_label=domain_label)
+
+
+def case_dsbn(hw=32, batch=4, domains=3, classes=2, c=3):
+    torch.manual_seed(SEED)
+    ref = _EncRec(c, classes, domains)
+    torch.manual_seed(SEED)
+    enc = U.init_unet_b(c, classes, norm="bn", decoder=False)
+    dec = U.init_rec_decoder(num_classes=classes, norm="dsbn", num_domains=domains)
+    st = {**{"enc." + k: v for k, v in enc.items()}, **{"dec." + k: v for k, v in dec.items()}}
+    assert_same_state(ref, st)
+    x = torch.rand(batch, c, hw, hw, generator=torch.Generator().manual_seed(SEED + 3)) * 2 - 1
+    dl = torch.tensor([2, 2, 0, 1])
+
+    def fwd(s, t):
+        e = {k[4:]: v for k, v in s.items() if k.startswith("enc.")}
+        d = {k[4:]: v for k, v in s.items() if k.startswith("dec.")}
+        return U.rec_decoder_forward(d, U.unet_b_encoder(e, t, True)[-1], dl, True)
+
+    run_model_case("dsbn_encrec", ref, st, fwd, x, classes, extra={"domain_label": dl})
+    # plain DSBN module semantics (dsbn.py:24-27): tuple return, bns[domain_label[0]] only
+    torch.manual_seed(SEED)
+    m = DomainSpecificBatchNorm2d(8, 3)
+    y, dl2 = m(torch.ones(2, 8, 4, 4), torch.tensor([1, 0]))
+    assert [int(b.num_batches_tracked) for b in m.bns] == [0, 1, 0] and dl2.tolist() == [1, 0]
+
+
+def case_losses():
+    fx = {}
+    g = torch.Generator().manual_seed(SEED + 11)
+    for C in (2, 3, 4):
+        dice = ref_losses.DiceLossWithMask(C)
+        logits = (torch.randn(2, C, 12, 10, generator=g) * 2).requires_grad_(True)
+        tgt = torch.randint(0, C, (2, 12, 10), generator=g)
+        msk = (torch.rand(2, 1, 12, 10, generator=g) > 0.5).float()
+        for tag, m in (("m", msk), ("n", None)):
+            ref = dice(logits, tgt.unsqueeze(1), mask=m, softmax=True)
+            (gr,) = torch.autograd.grad(ref, logits)
+            mine = S.dice_loss_with_mask(logits, tgt.unsqueeze(1), C, mask=m, softmax=True)
+            assert torch.equal(ref, mine)
+            fx[f"softmax_C{C}_{tag}/loss"], fx[f"softmax_C{C}_{tag}/grad"] = np_(ref), np_(gr)
+        fx[f"softmax_C{C}/logits"], fx[f"softmax_C{C}/target"], fx[f"softmax_C{C}/mask"] = np_(logits), np_(tgt), np_(msk)
+        # F8: class-0 dice term ignores the mask entirely
+        allzero = dice(logits, tgt.unsqueeze(1), mask=torch.zeros_like(msk), softmax=True)
+        fx[f"softmax_C{C}_zero_mask/loss"] = np_(allzero)
+    dice = ref_losses.DiceLossWithMask(2)
+    logits = (torch.randn(2, 2, 12, 10, generator=g) * 2).requires_grad_(True)
+    tgt = torch.randint(0, 2, (2, 2, 12, 10), generator=g).float()
+    msk = (torch.rand(2, 2, 12, 10, generator=g) > 0.5).float()
+    for tag, m in (("m", msk), ("n", None)):
+        ref = dice(logits, tgt.unsqueeze(1), mask=m, sigmoid=True, multi=True)
+        (gr,) = torch.autograd.grad(ref, logits)
+        assert torch.equal(ref, S.dice_loss_with_mask(logits, tgt.unsqueeze(1), 2, mask=m, sigmoid=True, multi=True))
+        fx[f"sigmoid_{tag}/loss"], fx[f"sigmoid_{tag}/grad"] = np_(ref), np_(gr)
+    fx["sigmoid/logits"], fx["sigmoid/target"], fx["sigmoid/mask"] = np_(logits), np_(tgt), np_(msk)
+    for cur in (0, 1, 37.0, 199, 200, 500):
+        assert S.sigmoid_rampup(cur, 200.0) == ref_ramps.sigmoid_rampup(cur, 200.0)
+        fx[f"rampup/{cur}"] = np.float64(ref_ramps.sigmoid_rampup(cur, 200.0))
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **fx)
+    print("losses: ok")
+
+
+def case_step(model, branch, n_channels, n_classes, hw, B, iter_num, bank):
+    """Whole step: the oracle glue driving REFERENCE modules/loss/SGD vs. the fully restated oracle."""
+    torch.manual_seed(SEED)
+    if model == "a":
+        ref_s, ref_t = ref_unet_a.UNet(n_channels, n_classes), ref_unet_a.UNet(n_channels, n_classes)
+        torch.manual_seed(SEED)
+        st_s, st_t = U.init_unet_a(n_channels, n_classes), U.init_unet_a(n_channels, n_classes)
+        fwd = lambda s, x: U.unet_a_forward(s, x, True)
+    else:
+        ref_s, ref_t = ref_unet_b.UNet(n_channels, n_classes), ref_unet_b.UNet(n_channels, n_classes)
+        torch.manual_seed(SEED)
+        st_s, st_t = U.init_unet_b(n_channels, n_classes), U.init_unet_b(n_channels, n_classes)
+        fwd = lambda s, x: U.unet_b_forward(s, x, True)
+    for p in ref_t.parameters():
+        p.detach_()
+    assert_same_state(ref_s, st_s), assert_same_state(ref_t, st_t)
+    batch = S.synthetic_batch(n_channels, n_classes, hw, hw, B, B, seed=SEED, branch=branch, bank=bank)
+    thr = 0.6 if branch == "softmax" else 0.55       # random-init nets are unconfident
+    kw = dict(n_classes=n_classes, branch=branch, iter_num=iter_num, max_iterations=30000, lr=0.03,
+              threshold=thr)
+    # --- reference side: real modules + real DiceLossWithMask + torch.optim.SGD -------------
+    ref_s.train(), ref_t.train()
+    opt = torch.optim.SGD(ref_s.parameters(), lr=0.03, momentum=0.9, weight_decay=0.0001)
+    dice = ref_losses.DiceLossWithMask(n_classes)
+    ce = torch.nn.CrossEntropyLoss(reduction="none") if branch == "softmax" else torch.nn.BCEWithLogitsLoss(reduction="none")
+    sm, sg, mu = (True, False, False) if branch == "softmax" else (False, True, True)
+    b = batch
+    img_box = b["box"].unsqueeze(1)
+    mix_img = b["cut_img"][b["choice"]]
+    with torch.no_grad():
+        t1 = ref_t(b["ulb_w"]); t2 = ref_t(S.mix(b["ulb_w"], mix_img, img_box)); t3 = ref_t(S.mix(mix_img, b["ulb_w"], img_box))
+        comp = S.compose(t1, t2, t3, b["box"], b["cut_label"], b["cut_mask"], b["choice"], thr, branch)
+    # the reference composes mask_ul/mask_lu with boolean-mask assignment (train.py:688-697);
+    # the oracle uses torch.where -- check the two formulations agree on this batch
+    m_ul, m_lu = comp["mask"].clone(), comp["mask"].clone()
+    sel = img_box.expand(m_ul.shape)
+    m_ul[sel == 1] = b["cut_mask"][b["choice"]][sel == 1]
+    m_lu[sel == 0] = b["cut_mask"][b["choice"]][sel == 0]
+    assert torch.equal(m_ul, comp["mask_ul"]) and torch.equal(m_lu, comp["mask_lu"])
+    ref_s(b["ulb_w"])
+    outs = [ref_s(b["lb_x"]), ref_s(S.mix(b["ulb_s"], b["move_transx"], img_box)),
+            ref_s(S.mix(b["move_transx"], b["ulb_s"], img_box)), ref_s(b["ulb_s"])]
+    tg = [(b["lb_mask"], None), (comp["pseudo_label_ul"], comp["mask_ul"]),
+          (comp["pseudo_label_lu"], comp["mask_lu"]), (comp["pseudo_label_w"], comp["mask_w"])]
+    terms = []
+    for o, (t, m) in zip(outs, tg):
+        c = ce(o, t)
+        if m is not None:
+            c = c * m.squeeze(1)
+        terms.append(c.mean() + dice(o, t.unsqueeze(1), mask=m, softmax=sm, sigmoid=sg, multi=mu))
+    cw = 1.0 * ref_ramps.sigmoid_rampup(iter_num // (30000 / 200.0), 200.0)
+    loss = terms[0] + cw * (terms[1] + terms[2] + cw * terms[3])
+    opt.zero_grad(); loss.backward(); opt.step()
+    alpha = min(1 - 1 / (iter_num + 1), 0.99)
+    for ep, p in zip(ref_t.parameters(), ref_s.parameters()):
+        ep.data.mul_(alpha).add_(p.data, alpha=1 - alpha)
+    # --- oracle side ------------------------------------------------------------------------
+    bufs = {}
+    out = S.ssl_step(fwd, st_s, st_t, bufs, batch, **kw)
+    assert torch.equal(out["loss"], loss.detach()), (out["loss"], loss)
+    for k in comp:
+        assert torch.equal(out[k], comp[k]), k
+    assert_same_state(ref_s, {k: v.detach() for k, v in st_s.items()})
+    assert_same_state(ref_t, {k: v.detach() for k, v in st_t.items()})
+    name = f"step_{model}_{branch}_c{n_channels}_k{n_classes}_{hw}_b{B}_it{iter_num}_bank{bank}"
+    fx = {"loss": np_(loss), "terms": np.array([t.item() for t in terms]), "cw": np.float64(cw),
+          "threshold": np.float64(thr), "mask_mean": np.float64(comp["mask"].mean().item())}
+    for k, v in comp.items():
+        fx["comp/" + k] = np_(v).astype(np.uint8) if v.dtype in (torch.int64,) or v.max() <= 1 else np_(v)
+    for k, v in out["logits"].items():
+        fx["logits/" + k] = np_(v)
+    for k, v in digest(ref_s.state_dict()).items():
+        fx["student_after/" + k] = v
+    for k, v in digest(ref_t.state_dict()).items():
+        fx["teacher_after/" + k] = v
+    for k, v in out["grads"].items():
+        fx["grad/" + k] = np.concatenate([[v.double().norm().item(), v.double().sum().item()], np_(v.flatten()[:6]).astype(np.float64)])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+    print(f"{name}: loss={loss.item():.6f} mask_mean={comp['mask'].mean().item():.3f} ok")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    case_losses()
+    case_unet_a(1, 2, 32, 2)
+    case_unet_a(3, 3, 32, 2)
+    case_unet_b(3, 3, 32, 2)
+    case_unet_b(1, 2, 48, 2)
+    case_dsbn()
+    case_step("a", "softmax", 1, 2, 32, 2, iter_num=0, bank=0)
+    case_step("a", "softmax", 1, 4, 32, 2, iter_num=15000, bank=2)
+    case_step("b", "softmax", 3, 3, 32, 2, iter_num=3000, bank=0)
+    case_step("b", "sigmoid", 3, 2, 32, 2, iter_num=3000, bank=2)
+
+
+if __name__ == "__main__":
+    main()
