@@ -1,0 +1,172 @@
+/* libustrun_sm100.so -- C ABI of the B200-native UST-RUN SSL train-step kernels.
+ *
+ * The reference (MQinghe/UST-RUN) is pure Python/PyTorch and has no FFI of its own; the boundary a
+ * maintainer binds is therefore "one entry point per library kernel the reference's hot path
+ * dispatches" (SURVEY.md section 2.2 K1-K16, section 8b).  Each declaration cites the reference
+ * call site it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless marked "host".
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - returns 0 on success, USTRUN_ERR_ARG (-1) on an argument/shape error, otherwise the
+ *     cudaError_t of the failed launch; `ustrun_last_error_string()` has the message.
+ *   - never allocates, frees or synchronises; workspaces are caller-provided.
+ *   - activations are NHWC with an explicit pixel pitch `ld*` in elements (so a tensor may be a
+ *     channel slice of a wider concat buffer); `dtype` selects fp32 (validation mode) or bf16.
+ *   - there is NO CPU path: every entry needs an sm_100 device.
+ */
+#ifndef USTRUN_H_
+#define USTRUN_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USTRUN_ABI_VERSION 1
+#define USTRUN_ERR_ARG (-1)
+
+enum { USTRUN_F32 = 0, USTRUN_BF16 = 1 };
+enum { USTRUN_ACT_NONE = 0, USTRUN_ACT_RELU = 1, USTRUN_ACT_LEAKY = 2 };
+enum { USTRUN_IMPL_SIMT = 0, USTRUN_IMPL_TCGEN05 = 1 };
+/* rows a per-channel partial-sum workspace must provide: float[USTRUN_MAX_PARTS][2][C] */
+#define USTRUN_MAX_PARTS 640
+
+int ustrun_abi_version(void);
+const char* ustrun_last_error_string(void);
+/* 1 if the current CUDA device is compute capability 10.x, 0 otherwise, <0 on CUDA error */
+int ustrun_device_supported(void);
+
+/* ---- layout / packing ------------------------------------------------------------------- */
+/* inputs arrive NCHW fp32 (dataloaders/custom_transforms.py:739-747) */
+int ustrun_nchw_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int H, int W, int ld_dst, void* stream);
+int ustrun_nhwc_to_nchw(const void* src, int dtype, int ld_src, float* dst, int B, int C, int H, int W, void* stream);
+/* nn.Conv2d weight OIHW fp32 -> wf[Cout][k*k][Cin] (forward) and wd[Cin][k*k flipped][Cout] (dgrad) */
+int ustrun_pack_conv_weight(const float* w, void* wf, void* wd, int dtype, int Cout, int Cin, int ksize, void* stream);
+/* nn.ConvTranspose2d(k2,s2) weight [Cin][Cout][2][2] -> wf[4][Cout][Cin], wd[Cin][4][Cout] */
+int ustrun_pack_convT_weight(const float* w, void* wf, void* wd, int dtype, int Cin, int Cout, void* stream);
+
+/* ---- convolutions (K1,K2,K3,K8,K10) ------------------------------------------------------- */
+/* nn.Conv2d 3x3 s1 p1 / 1x1 forward: unet_parts.py:16,19,74; unet.py:37-43,81,85,88,182.
+ * Also used for dgrad with the `wd` packing (autograd of the same call sites).
+ * y = conv(x) [+ bias]; if `partials` != NULL also writes per-channel (sum, sum of squares) of the
+ * fp32 results (before bias, before rounding) as float[*nparts][2][Cout] for train-mode BatchNorm.
+ * out_nchw_f32 != 0: y is a float NCHW tensor (the logits head) instead of NHWC `dtype`. */
+int ustrun_conv_fwd(int impl, const void* x, int ldx, const void* w_packed, const float* bias, void* y, int ldy,
+                    int dtype, int B, int H, int W, int Cin, int Cout, int ksize, int out_nchw_f32,
+                    float* partials, int* nparts_host, void* stream);
+/* dW[Cout][Cin][k][k] (fp32, OIHW like the nn.Parameter) (+)= sum_p dy[p][co] * x[p+tap][ci].
+ * accumulate != 0 adds to dw (gradient accumulation over the four loss branches, train.py:838). */
+int ustrun_conv_wgrad(int impl, const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate,
+                      int dtype, int B, int H, int W, int Cin, int Cout, int ksize, void* workspace,
+                      long long workspace_bytes, void* stream);
+long long ustrun_conv_wgrad_workspace_bytes(int impl, int B, int H, int W, int Cin, int Cout, int ksize);
+/* nn.ConvTranspose2d(k2,s2)+bias: unet_parts.py:53,57.  x is [B,H,W,Cin]; y is [B,2H,2W,Cout]. */
+int ustrun_convT2x2_fwd(int impl, const void* x, int ldx, const void* wf, const float* bias, void* y, int ldy,
+                        int dtype, int B, int H, int W, int Cin, int Cout, void* stream);
+int ustrun_convT2x2_dgrad(int impl, const void* dy, int lddy, const void* wd, void* dx, int lddx, int dtype,
+                          int B, int H, int W, int Cin, int Cout, void* stream);
+int ustrun_convT2x2_wgrad(int impl, const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate,
+                          int dtype, int B, int H, int W, int Cin, int Cout, void* workspace,
+                          long long workspace_bytes, void* stream);
+/* out[c] (+)= sum_p x[p][c]  (bias gradients of convT / head convs) */
+int ustrun_channel_sum(const void* x, int ldx, int dtype, long long npix, int C, float* out, int accumulate,
+                       float* workspace, void* stream);
+
+/* ---- BatchNorm / DSBN (K4,K5) : unet_parts.py:17,20; unet.py:19; dsbn.py:11,24-27 ---------- */
+/* sums[2][C] = sum over parts (for cross-rank reduction before finalize) */
+int ustrun_bn_reduce_partials(const float* partials, int nparts, int C, float* sums, void* stream);
+/* training: batch statistics from partials (nparts rows), running-stat update (unbiased var,
+ * momentum), num_batches_tracked += 1; eval: running statistics.  conv_bias (nullable) is the
+ * bias of the preceding conv (UNet-B), which the conv kernels do not add.  Outputs per channel:
+ * scale, shift (y = x*scale + shift), mean, rstd (saved for backward). */
+int ustrun_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
+                       const float* conv_bias, float* running_mean, float* running_var, long long* num_batches_tracked,
+                       float momentum, float eps, int training, float* scale, float* shift, float* mean, float* rstd,
+                       void* stream);
+/* y = act(x*scale+shift); optional 2x2 max-pooled copy (nn.MaxPool2d(2): unet_parts.py:34, unet.py:45) */
+int ustrun_bn_act_fwd(const void* x, int ldx, const float* scale, const float* shift, int act, void* y, int ldy,
+                      void* pooled, int ldp, int dtype, int B, int H, int W, int C, void* stream);
+/* partials[*nparts][2][C] of (sum g', sum g'*xhat), g' = g * act'(x*scale+shift) */
+int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const float* mean, const float* rstd,
+                         const float* scale, const float* shift, int act, int dtype, long long npix, int C,
+                         float* partials, int* nparts_host, void* stream);
+/* dgamma/dbeta (+)= ; coef[3][C] = (gamma*rstd, sum g'/count, sum g' xhat/count) */
+int ustrun_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* rstd,
+                           float* dgamma, float* dbeta, int accumulate, float* coef, void* stream);
+int ustrun_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, const float* mean, const float* rstd,
+                        const float* scale, const float* shift, const float* coef, int act, void* dx, int lddx,
+                        int dtype, long long npix, int C, void* stream);
+/* gout = gskip (nullable) + unpool(dpool) routed to the first max of each 2x2 window of y */
+int ustrun_maxpool_bwd(const void* y, int ldy, const void* dpool, int ldp, const void* gskip, int ldgs, void* gout,
+                       int ldgo, int dtype, int B, int H, int W, int C, void* stream);
+/* nn.Upsample(x2, bilinear): unet.py:84,127 (align_corners=False), unet_parts.py:50 (True) */
+int ustrun_upsample2x_fwd(const void* x, int ldx, void* y, int ldy, int dtype, int B, int H, int W, int C,
+                          int align_corners, void* stream);
+int ustrun_upsample2x_bwd(const void* dy, int lddy, void* dx, int lddx, int dtype, int B, int H, int W, int C,
+                          int align_corners, void* stream);
+
+/* ---- pseudo labels (K12): train.py:649-697, train_mnms.py:595-623 -------------------------- */
+/* softmax branch.  t1,t2,t3 (teacher) and s0 (student, nullable) are fp32 NCHW logits [Bu,C,H,W];
+ * box, cut_label, cut_mask are uint8 ([Bu,H,W], [Nc,H,W], [Nc,H,W]); choice int32[Bu].
+ * Outputs are uint8 [Bu,H,W]. stats (nullable) float[2]: sum(mask), sum(mask_w) for logging. */
+int ustrun_pseudo_label_softmax(const float* t1, const float* t2, const float* t3, const float* s0,
+                                const uint8_t* box, const uint8_t* cut_label, const uint8_t* cut_mask,
+                                const int* choice, float threshold, int Bu, int C, int H, int W,
+                                uint8_t* pl, uint8_t* mask, uint8_t* pl_w, uint8_t* mask_w, uint8_t* pl_ul,
+                                uint8_t* mask_ul, uint8_t* pl_lu, uint8_t* mask_lu, uint8_t* stu_pl, void* stream);
+/* sigmoid (fundus) branch: everything is per element [Bu,C,H,W]; box stays [Bu,H,W].
+ * thr_hi = float(threshold), thr_lo = float(1-threshold) as torch casts them (train.py:651). */
+int ustrun_pseudo_label_sigmoid(const float* t1, const float* t2, const float* t3, const float* s0,
+                                const uint8_t* box, const uint8_t* cut_label, const uint8_t* cut_mask,
+                                const int* choice, float thr_hi, float thr_lo, int Bu, int C, int H, int W,
+                                uint8_t* pl, uint8_t* mask, uint8_t* pl_w, uint8_t* mask_w, uint8_t* pl_ul,
+                                uint8_t* mask_ul, uint8_t* pl_lu, uint8_t* mask_lu, uint8_t* stu_pl, void* stream);
+/* a*(1-box)+b*box on images (train.py:644,646,689,692); fp32 NCHW in, NHWC `dtype` out */
+int ustrun_mix_to_nhwc(const float* a, const float* b, const int* b_index, const uint8_t* box, void* dst, int ld_dst,
+                       int dtype, int B, int C, int H, int W, void* stream);
+
+/* ---- CE + Dice (K13,K14): train.py:816-838, utils/losses.py:194-268 ------------------------- */
+/* Pass 1 reduces (3C+1) scalars; the finalize stage (same call) writes
+ *   loss_out[0] = ce_w * mean_all(CE*mask) + dice_w * DiceLossWithMask   (either weight may be 0)
+ *   loss_out[1] = CE part, loss_out[2] = Dice part, and coef[] for pass 2.
+ * target uint8 [B,H,W]; mask uint8 [B,H,W] or NULL; class_weight float[C] or NULL (losses.py:251).
+ * workspace: float[USTRUN_MAX_PARTS*(3C+1)]; coef: float[4*C+4]. */
+int ustrun_ce_dice_softmax_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
+                               int W, float ce_w, float dice_w, const float* class_weight, float* workspace,
+                               float* coef, float* loss_out, void* stream);
+/* dlogits (+)= gscale * (*upstream, nullable => 1) * dLoss/dlogits */
+int ustrun_ce_dice_softmax_bwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
+                               int W, const float* coef, const float* upstream, float gscale, float* dlogits,
+                               int accumulate, void* stream);
+/* sigmoid/multi (fundus) branch: BCEWithLogits*mask mean + one global Dice (losses.py:244-249);
+ * target, mask uint8 [B,C,H,W] */
+int ustrun_bce_dice_sigmoid_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
+                                int W, float ce_w, float dice_w, float* workspace, float* coef, float* loss_out,
+                                void* stream);
+int ustrun_bce_dice_sigmoid_bwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
+                                int W, const float* coef, const float* upstream, float gscale, float* dlogits,
+                                int accumulate, void* stream);
+
+/* ---- SGD + EMA (K15,K16): train.py:512,840-851,87-93 ---------------------------------------- */
+typedef struct {
+  float* p;      /* student parameter (fp32) */
+  float* g;      /* gradient or NULL (parameter skipped, like torch SGD with grad=None) */
+  float* buf;    /* momentum buffer */
+  float* ema;    /* teacher parameter or NULL */
+  long long n;   /* elements */
+  int first;     /* 1: momentum buffer not initialised yet (buf = g) */
+  int pad;
+} ustrun_param_t;
+/* One launch over all tensors. blk_tensor[i], blk_offset[i]: tensor index and element offset of
+ * block i's chunk (chunk = USTRUN_OPT_CHUNK elements).  g <- g + wd*p; buf <- first? g : mu*buf+g;
+ * p <- p - lr*buf; ema <- alpha*ema + (1-alpha)*p.  do_sgd/do_ema select the halves. */
+#define USTRUN_OPT_CHUNK 4096
+int ustrun_sgd_ema_multi(const ustrun_param_t* table, const int* blk_tensor, const long long* blk_offset, int nblocks,
+                         float lr, float momentum, float weight_decay, float alpha, float grad_scale, int do_sgd,
+                         int do_ema, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USTRUN_H_ */

@@ -1,0 +1,109 @@
+// extern "C" convolution entry points: argument checks + dispatch to the CUDA-core (simt_conv.cu)
+// or tcgen05 (tc_conv.cu) implementation.  `impl` is the caller's explicit choice -- there is no
+// silent fallback: an unsupported (impl, shape, dtype) combination is an argument error.
+#include "common.cuh"
+
+namespace ustrun {
+template <typename T>
+int simt_conv_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, float* y_nchw, ConvGeom g, float* partials,
+                     int* nparts_host, cudaStream_t st);
+template <typename T>
+int simt_wgrad_launch(const void* a, int lda, const void* b, int ldb, float* dw, int accumulate, ConvGeom g, int Mo, int Nin, void* workspace,
+                      long long ws_bytes, cudaStream_t st);
+long long simt_wgrad_ws_bytes(long long P, int Mo, int Nin, int taps);
+
+int tc_conv_fwd(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize,
+                float* partials, int* nparts_host, cudaStream_t st);
+int tc_convT_fwd(const void* x, int ldx, const void* wf, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
+int tc_convT_dgrad(const void* dy, int lddy, const void* wd, void* dx, int lddx, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
+int tc_conv_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout, int ksize,
+                  void* workspace, long long ws_bytes, cudaStream_t st);
+long long tc_conv_wgrad_ws(int B, int H, int W, int Cin, int Cout, int ksize);
+int tc_convT_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout,
+                   void* workspace, long long ws_bytes, cudaStream_t st);
+long long tc_convT_wgrad_ws(int B, int H, int W, int Cin, int Cout);
+}  // namespace ustrun
+
+using namespace ustrun;
+
+#define CHECK_COMMON(name)                                                                                            \
+  USTRUN_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, name ": empty shape");                               \
+  USTRUN_REQUIRE(dtype == USTRUN_F32 || dtype == USTRUN_BF16, name ": bad dtype");                                    \
+  USTRUN_REQUIRE(impl == USTRUN_IMPL_SIMT || (impl == USTRUN_IMPL_TCGEN05 && dtype == USTRUN_BF16), name ": tcgen05 path is bf16 only")
+
+extern "C" {
+
+int ustrun_conv_fwd(int impl, const void* x, int ldx, const void* w_packed, const float* bias, void* y, int ldy, int dtype, int B, int H,
+                    int W, int Cin, int Cout, int ksize, int out_nchw_f32, float* partials, int* nparts_host, void* stream) {
+  CHECK_COMMON("conv_fwd");
+  USTRUN_REQUIRE(x && w_packed && y && (ksize == 1 || ksize == 3) && ldx >= Cin, "conv_fwd: bad args");
+  USTRUN_REQUIRE(!partials || nparts_host, "conv_fwd: partials needs nparts_host");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == USTRUN_IMPL_TCGEN05) {
+    USTRUN_REQUIRE(!out_nchw_f32, "conv_fwd: tcgen05 path writes NHWC bf16 only");
+    return tc_conv_fwd(x, ldx, w_packed, bias, y, ldy, B, H, W, Cin, Cout, ksize, partials, nparts_host, st);
+  }
+  ConvGeom g{B, H, W, Cin, Cout, ksize, 0, -1};
+  float* ynchw = out_nchw_f32 ? (float*)y : nullptr;
+  if (dtype == USTRUN_F32) return simt_conv_launch<float>(x, ldx, w_packed, bias, y, ldy, ynchw, g, partials, nparts_host, st);
+  return simt_conv_launch<__nv_bfloat16>(x, ldx, w_packed, bias, y, ldy, ynchw, g, partials, nparts_host, st);
+}
+
+long long ustrun_conv_wgrad_workspace_bytes(int impl, int B, int H, int W, int Cin, int Cout, int ksize) {
+  // ksize 2 = ConvTranspose2d(k2,s2): Mo = Cin, N = 4*Cout
+  if (ksize == 2) return impl == USTRUN_IMPL_TCGEN05 ? tc_convT_wgrad_ws(B, H, W, Cin, Cout) : simt_wgrad_ws_bytes((long long)B * H * W, Cin, Cout, 4);
+  if (impl == USTRUN_IMPL_TCGEN05) return tc_conv_wgrad_ws(B, H, W, Cin, Cout, ksize);
+  return simt_wgrad_ws_bytes((long long)B * H * W, Cout, Cin, ksize * ksize);
+}
+
+int ustrun_conv_wgrad(int impl, const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int dtype, int B, int H, int W,
+                      int Cin, int Cout, int ksize, void* workspace, long long workspace_bytes, void* stream) {
+  CHECK_COMMON("conv_wgrad");
+  USTRUN_REQUIRE(dy && x && dw && (ksize == 1 || ksize == 3), "conv_wgrad: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == USTRUN_IMPL_TCGEN05) return tc_conv_wgrad(dy, lddy, x, ldx, dw, accumulate, B, H, W, Cin, Cout, ksize, workspace, workspace_bytes, st);
+  ConvGeom g{B, H, W, Cin, Cout, ksize, 0, -1};
+  if (dtype == USTRUN_F32) return simt_wgrad_launch<float>(dy, lddy, x, ldx, dw, accumulate, g, Cout, Cin, workspace, workspace_bytes, st);
+  return simt_wgrad_launch<__nv_bfloat16>(dy, lddy, x, ldx, dw, accumulate, g, Cout, Cin, workspace, workspace_bytes, st);
+}
+
+int ustrun_convT2x2_fwd(int impl, const void* x, int ldx, const void* wf, const float* bias, void* y, int ldy, int dtype, int B, int H, int W,
+                        int Cin, int Cout, void* stream) {
+  CHECK_COMMON("convT2x2_fwd");
+  USTRUN_REQUIRE(x && wf && y, "convT2x2_fwd: null arg");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == USTRUN_IMPL_TCGEN05) return tc_convT_fwd(x, ldx, wf, bias, y, ldy, B, H, W, Cin, Cout, st);
+  const size_t esz = dtype == USTRUN_F32 ? 4 : 2;
+  for (int ij = 0; ij < 4; ++ij) {
+    ConvGeom g{B, H, W, Cin, Cout, 1, 0, ij};
+    const void* wij = (const char*)wf + (size_t)ij * Cout * Cin * esz;
+    int rc = dtype == USTRUN_F32 ? simt_conv_launch<float>(x, ldx, wij, bias, y, ldy, nullptr, g, nullptr, nullptr, st)
+                                 : simt_conv_launch<__nv_bfloat16>(x, ldx, wij, bias, y, ldy, nullptr, g, nullptr, nullptr, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int ustrun_convT2x2_dgrad(int impl, const void* dy, int lddy, const void* wd, void* dx, int lddx, int dtype, int B, int H, int W, int Cin,
+                          int Cout, void* stream) {
+  CHECK_COMMON("convT2x2_dgrad");
+  USTRUN_REQUIRE(dy && wd && dx, "convT2x2_dgrad: null arg");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == USTRUN_IMPL_TCGEN05) return tc_convT_dgrad(dy, lddy, wd, dx, lddx, B, H, W, Cin, Cout, st);
+  ConvGeom g{B, H, W, /*gathered channels*/ Cout, /*outputs*/ Cin, 1, 1, -1};
+  if (dtype == USTRUN_F32) return simt_conv_launch<float>(dy, lddy, wd, nullptr, dx, lddx, nullptr, g, nullptr, nullptr, st);
+  return simt_conv_launch<__nv_bfloat16>(dy, lddy, wd, nullptr, dx, lddx, nullptr, g, nullptr, nullptr, st);
+}
+
+int ustrun_convT2x2_wgrad(int impl, const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int dtype, int B, int H, int W,
+                          int Cin, int Cout, void* workspace, long long workspace_bytes, void* stream) {
+  CHECK_COMMON("convT2x2_wgrad");
+  USTRUN_REQUIRE(dy && x && dw, "convT2x2_wgrad: null arg");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == USTRUN_IMPL_TCGEN05) return tc_convT_wgrad(dy, lddy, x, ldx, dw, accumulate, B, H, W, Cin, Cout, workspace, workspace_bytes, st);
+  ConvGeom g{B, H, W, Cout, Cin, 1, 1, -1};
+  if (dtype == USTRUN_F32) return simt_wgrad_launch<float>(x, ldx, dy, lddy, dw, accumulate, g, Cin, Cout, workspace, workspace_bytes, st);
+  return simt_wgrad_launch<__nv_bfloat16>(x, ldx, dy, lddy, dw, accumulate, g, Cin, Cout, workspace, workspace_bytes, st);
+}
+
+}  // extern "C"

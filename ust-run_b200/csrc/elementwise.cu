@@ -1,0 +1,587 @@
+// Memory-bound kernels of the UNet forward/backward: layout converters, weight packing, BatchNorm
+// finalize/apply/backward, max-pool backward, bilinear x2 up-sampling, per-channel sums.
+// All are HBM-bound: 128-bit vector accesses along the NHWC channel axis, warp/block reductions,
+// two-stage (partials -> finalize) deterministic sums, no atomics.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace ustrun {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+const char* last_error() { return g_err; }
+
+#define DISPATCH_DTYPE(dtype, ...)                                   \
+  if ((dtype) == USTRUN_F32) {                                       \
+    using T = float;                                                 \
+    __VA_ARGS__;                                                     \
+  } else if ((dtype) == USTRUN_BF16) {                               \
+    using T = __nv_bfloat16;                                         \
+    __VA_ARGS__;                                                     \
+  } else {                                                           \
+    set_error("bad dtype %d", (int)(dtype));                         \
+    return USTRUN_ERR_ARG;                                           \
+  }
+
+static inline int grid_for(long long items, int threads, int cap = 148 * 16) {
+  long long b = (items + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)(b > cap ? cap : b);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------
+// src [B][C][HW] fp32 -> dst [B][HW][ld] T, 32x32 smem transpose tiles
+template <typename T>
+__global__ void k_nchw_to_nhwc(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int ld) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[((size_t)b * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) dst[((size_t)b * HW + p) * ld + c] = from_f<T>(tile[threadIdx.x][i]);
+  }
+}
+template <typename T>
+__global__ void k_nhwc_to_nchw(const T* __restrict__ src, float* __restrict__ dst, int C, int HW, int ld) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? to_f(src[((size_t)b * HW + p) * ld + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    if (p < HW && c < C) dst[((size_t)b * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+template <typename T>
+__global__ void k_pack_conv(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cout, int Cin, int taps) {
+  long long n = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps);
+    int ci = (int)((i / taps) % Cin);
+    int co = (int)(i / ((long long)taps * Cin));
+    float v = w[i];                                            // OIHW: ((co*Cin+ci)*taps + t)
+    if (wf) wf[((size_t)co * taps + t) * Cin + ci] = from_f<T>(v);
+    if (wd) wd[((size_t)ci * taps + (taps - 1 - t)) * Cout + co] = from_f<T>(v);
+  }
+}
+// ConvTranspose2d weight [Cin][Cout][2][2]
+template <typename T>
+__global__ void k_pack_convT(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cin, int Cout) {
+  long long n = (long long)Cin * Cout * 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int ij = (int)(i % 4);
+    int co = (int)((i / 4) % Cout);
+    int ci = (int)(i / (4LL * Cout));
+    float v = w[i];
+    if (wf) wf[((size_t)ij * Cout + co) * Cin + ci] = from_f<T>(v);
+    if (wd) wd[((size_t)ci * 4 + ij) * Cout + co] = from_f<T>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm
+// ------------------------------------------------------------------------------------------
+__global__ void k_bn_reduce_partials(const float* __restrict__ partials, int nparts, int C, float* __restrict__ sums) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * C) return;
+  double s = 0.0;
+  for (int r = 0; r < nparts; ++r) s += (double)partials[(size_t)r * 2 * C + i];
+  sums[i] = (float)s;
+}
+
+__global__ void k_bn_finalize(const float* __restrict__ partials, int nparts, int C, double count,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              const float* __restrict__ conv_bias, float* running_mean, float* running_var,
+                              long long* nbt, float momentum, float eps, int training, float* scale, float* shift,
+                              float* mean_out, float* rstd_out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt) *nbt += 1;
+  if (c >= C) return;
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  float cb = conv_bias ? conv_bias[c] : 0.f;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < nparts; ++r) {
+      s += (double)partials[(size_t)r * 2 * C + c];
+      q += (double)partials[(size_t)r * 2 * C + C + c];
+    }
+    double m = s / count;
+    double var = q / count - m * m;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float mf = (float)m;
+    scale[c] = g * rstd;
+    shift[c] = b - mf * g * rstd;                    // conv bias cancels in train mode
+    mean_out[c] = mf;
+    rstd_out[c] = rstd;
+    if (running_mean) {
+      double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mf + cb);
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    float rstd = rsqrtf(running_var[c] + eps);
+    rstd = 1.0f / sqrtf(running_var[c] + eps);
+    scale[c] = g * rstd;
+    shift[c] = b + (cb - running_mean[c]) * g * rstd;
+    mean_out[c] = running_mean[c] - cb;
+    rstd_out[c] = rstd;
+  }
+}
+
+template <typename T>
+__global__ void k_bn_act(const T* __restrict__ x, int ldx, const float* __restrict__ scale, const float* __restrict__ shift,
+                         int act, T* __restrict__ y, int ldy, long long npix, int C) {
+  int CG = C >> 3;
+  long long n = npix * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(i % CG);
+    long long p = i / CG;
+    float v[8], sc[8], sh[8];
+    Vec8<T>::load(x + p * ldx + cg * 8, v);
+    Vec8<float>::load(scale + cg * 8, sc);
+    Vec8<float>::load(shift + cg * 8, sh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = act_fwd(fmaf(v[k], sc[k], sh[k]), act);
+    Vec8<T>::store(y + p * ldy + cg * 8, v);
+  }
+}
+
+// BN-apply + activation + 2x2 max pool: one thread = one 2x2 quad x 8 channels
+template <typename T>
+__global__ void k_bn_act_pool(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
+                              const float* __restrict__ shift, int act, T* __restrict__ y, int ldy, T* __restrict__ pooled,
+                              int ldp, int B, int H, int W, int C) {
+  int CG = C >> 3, Hp = H >> 1, Wp = W >> 1;
+  long long n = (long long)B * Hp * Wp * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(i % CG);
+    long long q = i / CG;
+    int wp = (int)(q % Wp);
+    int hp = (int)((q / Wp) % Hp);
+    int b = (int)(q / ((long long)Wp * Hp));
+    float sc[8], sh[8], m[8];
+    Vec8<float>::load(scale + cg * 8, sc);
+    Vec8<float>::load(shift + cg * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      long long p = ((long long)b * H + (hp * 2 + (j >> 1))) * W + (wp * 2 + (j & 1));
+      float v[8];
+      Vec8<T>::load(x + p * ldx + cg * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] = act_fwd(fmaf(v[k], sc[k], sh[k]), act);
+        // pool over the values as stored (rounded to T), like pooling the stored tensor
+        float r = to_f(from_f<T>(v[k]));
+        m[k] = (j == 0) ? r : fmaxf(m[k], r);
+      }
+      Vec8<T>::store(y + p * ldy + cg * 8, v);
+    }
+    Vec8<T>::store(pooled + q * ldp + cg * 8, m);
+  }
+}
+
+// partial sums of (g', g'*xhat) per channel. 256 threads; thread owns channel group tid % CG.
+template <typename T>
+__global__ void k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ldx,
+                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const float* __restrict__ scale, const float* __restrict__ shift, int act, long long npix,
+                                int C, float* __restrict__ partials) {
+  extern __shared__ float sm[];   // [256][16]
+  int CG = C >> 3;
+  int tid = threadIdx.x;
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  if (CG <= 256) {
+    int cg = tid % CG;
+    int lanes = 256 / CG;                       // pixel lanes per block
+    float mu[8], rs[8], sc[8], sh[8];
+    Vec8<float>::load(mean + cg * 8, mu);
+    Vec8<float>::load(rstd + cg * 8, rs);
+    Vec8<float>::load(scale + cg * 8, sc);
+    Vec8<float>::load(shift + cg * 8, sh);
+    for (long long p = (long long)blockIdx.x * lanes + tid / CG; p < npix; p += (long long)gridDim.x * lanes) {
+      float gv[8], xv[8];
+      Vec8<T>::load(g + p * ldg + cg * 8, gv);
+      Vec8<T>::load(x + p * ldx + cg * 8, xv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float gp = gv[k] * act_grad(fmaf(xv[k], sc[k], sh[k]), act);
+        acc[k] += gp;
+        acc[8 + k] += gp * ((xv[k] - mu[k]) * rs[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) sm[tid * 16 + k] = acc[k];
+  __syncthreads();
+  int lanes = 256 / CG;
+  for (int o = tid; o < 2 * C; o += 256) {
+    int which = o / C, c = o % C;
+    int cg = c >> 3, k = (c & 7) + which * 8;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += sm[(l * CG + cg) * 16 + k];
+    partials[(size_t)blockIdx.x * 2 * C + o] = s;
+  }
+}
+
+__global__ void k_bn_bwd_finalize(const float* __restrict__ partials, int nparts, int C, double count,
+                                  const float* __restrict__ gamma, const float* __restrict__ rstd, float* dgamma,
+                                  float* dbeta, int accumulate, float* coef) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = 0; r < nparts; ++r) {
+    s1 += (double)partials[(size_t)r * 2 * C + c];
+    s2 += (double)partials[(size_t)r * 2 * C + C + c];
+  }
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
+  float g = gamma ? gamma[c] : 1.f;
+  coef[c] = g * rstd[c];
+  coef[C + c] = (float)(s1 / count);
+  coef[2 * C + c] = (float)(s2 / count);
+}
+
+template <typename T>
+__global__ void k_bn_bwd_apply(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ldx,
+                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                               const float* __restrict__ scale, const float* __restrict__ shift,
+                               const float* __restrict__ coef, int act, T* __restrict__ dx, int lddx, long long npix, int C) {
+  int CG = C >> 3;
+  long long n = npix * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(i % CG);
+    long long p = i / CG;
+    float gv[8], xv[8], mu[8], rs[8], sc[8], sh[8], a[8], b[8], d[8], o[8];
+    Vec8<T>::load(g + p * ldg + cg * 8, gv);
+    Vec8<T>::load(x + p * ldx + cg * 8, xv);
+    Vec8<float>::load(mean + cg * 8, mu);
+    Vec8<float>::load(rstd + cg * 8, rs);
+    Vec8<float>::load(scale + cg * 8, sc);
+    Vec8<float>::load(shift + cg * 8, sh);
+    Vec8<float>::load(coef + cg * 8, a);
+    Vec8<float>::load(coef + C + cg * 8, b);
+    Vec8<float>::load(coef + 2 * C + cg * 8, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float gp = gv[k] * act_grad(fmaf(xv[k], sc[k], sh[k]), act);
+      float xh = (xv[k] - mu[k]) * rs[k];
+      o[k] = a[k] * (gp - b[k] - xh * d[k]);
+    }
+    Vec8<T>::store(dx + p * lddx + cg * 8, o);
+  }
+}
+
+template <typename T>
+__global__ void k_maxpool_bwd(const T* __restrict__ y, int ldy, const T* __restrict__ dpool, int ldp,
+                              const T* __restrict__ gskip, int ldgs, T* __restrict__ gout, int ldgo, int B, int H, int W, int C) {
+  int CG = C >> 3, Hp = H >> 1, Wp = W >> 1;
+  long long n = (long long)B * Hp * Wp * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(i % CG);
+    long long q = i / CG;
+    int wp = (int)(q % Wp);
+    int hp = (int)((q / Wp) % Hp);
+    int b = (int)(q / ((long long)Wp * Hp));
+    float v[4][8], dp[8];
+    long long p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p[j] = ((long long)b * H + (hp * 2 + (j >> 1))) * W + (wp * 2 + (j & 1));
+      Vec8<T>::load(y + p[j] * ldy + cg * 8, v[j]);
+    }
+    Vec8<T>::load(dpool + q * ldp + cg * 8, dp);
+    int arg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int a = 0;
+      float m = v[0][k];
+#pragma unroll
+      for (int j = 1; j < 4; ++j)
+        if (v[j][k] > m) { m = v[j][k]; a = j; }      // strict > keeps the first max (ATen max_pool2d)
+      arg[k] = a;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float o[8];
+      if (gskip) Vec8<T>::load(gskip + p[j] * ldgs + cg * 8, o);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += (arg[k] == j) ? dp[k] : 0.f;
+      Vec8<T>::store(gout + p[j] * ldgo + cg * 8, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bilinear x2 (ATen upsample_bilinear2d index rule: area_pixel_compute_source_index)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(int o, int in_size, int out_size, int align, int& i0, int& i1, float& l0, float& l1) {
+  float r;
+  if (align) {
+    float sc = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+    r = sc * o;
+  } else {
+    r = 0.5f * (o + 0.5f) - 0.5f;
+    if (r < 0.f) r = 0.f;
+  }
+  i0 = (int)r;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = r - (float)i0;
+  l0 = 1.f - l1;
+}
+
+template <typename T>
+__global__ void k_upsample2x_fwd(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int B, int H, int W, int C, int align) {
+  int CG = C >> 3, Ho = 2 * H, Wo = 2 * W;
+  long long n = (long long)B * Ho * Wo * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(i % CG);
+    long long q = i / CG;
+    int ow = (int)(q % Wo);
+    int oh = (int)((q / Wo) % Ho);
+    int b = (int)(q / ((long long)Wo * Ho));
+    int h0, h1, w0, w1;
+    float lh0, lh1, lw0, lw1;
+    src_index(oh, H, Ho, align, h0, h1, lh0, lh1);
+    src_index(ow, W, Wo, align, w0, w1, lw0, lw1);
+    const T* base = x + (size_t)b * H * W * ldx + cg * 8;
+    float a[8], bb[8], c[8], d[8], o[8];
+    Vec8<T>::load(base + ((size_t)h0 * W + w0) * ldx, a);
+    Vec8<T>::load(base + ((size_t)h0 * W + w1) * ldx, bb);
+    Vec8<T>::load(base + ((size_t)h1 * W + w0) * ldx, c);
+    Vec8<T>::load(base + ((size_t)h1 * W + w1) * ldx, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = lh0 * (lw0 * a[k] + lw1 * bb[k]) + lh1 * (lw0 * c[k] + lw1 * d[k]);
+    Vec8<T>::store(y + q * ldy + cg * 8, o);
+  }
+}
+
+// gather form of the backward: every input pixel collects from the <=5x5 outputs that can touch it
+template <typename T>
+__global__ void k_upsample2x_bwd(const T* __restrict__ dy, int lddy, T* __restrict__ dx, int lddx, int B, int H, int W, int C, int align) {
+  int CG = C >> 3, Ho = 2 * H, Wo = 2 * W;
+  long long n = (long long)B * H * W * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(i % CG);
+    long long q = i / CG;
+    int w = (int)(q % W);
+    int h = (int)((q / W) % H);
+    int b = (int)(q / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    int oh_lo, oh_hi, ow_lo, ow_hi;
+    if (align) { oh_lo = 0; oh_hi = Ho - 1; ow_lo = 0; ow_hi = Wo - 1;
+      // align_corners: outputs touching row h lie within [2h-2, 2h+3] as well (scale < 1)
+      oh_lo = max(0, 2 * h - 2); oh_hi = min(Ho - 1, 2 * h + 3); ow_lo = max(0, 2 * w - 2); ow_hi = min(Wo - 1, 2 * w + 3);
+    } else { oh_lo = max(0, 2 * h - 2); oh_hi = min(Ho - 1, 2 * h + 2); ow_lo = max(0, 2 * w - 2); ow_hi = min(Wo - 1, 2 * w + 2); }
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      int h0, h1; float lh0, lh1;
+      src_index(oh, H, Ho, align, h0, h1, lh0, lh1);
+      float wh = (h0 == h ? lh0 : 0.f) + (h1 == h ? lh1 : 0.f);
+      if (wh == 0.f) continue;
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        int w0, w1; float lw0, lw1;
+        src_index(ow, W, Wo, align, w0, w1, lw0, lw1);
+        float ww = (w0 == w ? lw0 : 0.f) + (w1 == w ? lw1 : 0.f);
+        if (ww == 0.f) continue;
+        float g[8];
+        Vec8<T>::load(dy + (((size_t)b * Ho + oh) * Wo + ow) * lddy + cg * 8, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += wh * ww * g[k];
+      }
+    }
+    Vec8<T>::store(dx + q * lddx + cg * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-channel sums (bias gradients)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_channel_sum_partial(const T* __restrict__ x, int ldx, long long npix, int C, float* __restrict__ part) {
+  __shared__ float sm[8][33];
+  int c = blockIdx.y * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < C)
+    for (long long p = (long long)blockIdx.x * 8 + threadIdx.y; p < npix; p += (long long)gridDim.x * 8) s += to_f(x[p * ldx + c]);
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+    part[(size_t)blockIdx.x * C + c] = t;
+  }
+}
+__global__ void k_channel_sum_final(const float* __restrict__ part, int nparts, int C, float* out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int r = 0; r < nparts; ++r) s += (double)part[(size_t)r * C + c];
+  out[c] = (accumulate ? out[c] : 0.f) + (float)s;
+}
+
+}  // namespace ustrun
+
+using namespace ustrun;
+
+extern "C" {
+
+int ustrun_abi_version(void) { return USTRUN_ABI_VERSION; }
+const char* ustrun_last_error_string(void) { return ustrun::last_error(); }
+int ustrun_device_supported(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return -(int)e; }
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) { set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e)); return -(int)e; }
+  return major == 10 ? 1 : 0;
+}
+
+int ustrun_nchw_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int H, int W, int ld_dst, void* stream) {
+  USTRUN_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0 && ld_dst >= C, "nchw_to_nhwc: bad args");
+  dim3 grid(ceil_div((long long)H * W, 32), ceil_div(C, 32), B), block(32, 8);
+  DISPATCH_DTYPE(dtype, (k_nchw_to_nhwc<T><<<grid, block, 0, (cudaStream_t)stream>>>(src, (T*)dst, C, H * W, ld_dst)));
+  return check_launch("nchw_to_nhwc");
+}
+int ustrun_nhwc_to_nchw(const void* src, int dtype, int ld_src, float* dst, int B, int C, int H, int W, void* stream) {
+  USTRUN_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0 && ld_src >= C, "nhwc_to_nchw: bad args");
+  dim3 grid(ceil_div((long long)H * W, 32), ceil_div(C, 32), B), block(32, 8);
+  DISPATCH_DTYPE(dtype, (k_nhwc_to_nchw<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)src, dst, C, H * W, ld_src)));
+  return check_launch("nhwc_to_nchw");
+}
+int ustrun_pack_conv_weight(const float* w, void* wf, void* wd, int dtype, int Cout, int Cin, int ksize, void* stream) {
+  USTRUN_REQUIRE(w && (wf || wd) && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), "pack_conv_weight: bad args");
+  long long n = (long long)Cout * Cin * ksize * ksize;
+  DISPATCH_DTYPE(dtype, (k_pack_conv<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (T*)wf, (T*)wd, Cout, Cin, ksize * ksize)));
+  return check_launch("pack_conv_weight");
+}
+int ustrun_pack_convT_weight(const float* w, void* wf, void* wd, int dtype, int Cin, int Cout, void* stream) {
+  USTRUN_REQUIRE(w && (wf || wd) && Cout > 0 && Cin > 0, "pack_convT_weight: bad args");
+  long long n = (long long)Cout * Cin * 4;
+  DISPATCH_DTYPE(dtype, (k_pack_convT<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (T*)wf, (T*)wd, Cin, Cout)));
+  return check_launch("pack_convT_weight");
+}
+
+int ustrun_bn_reduce_partials(const float* partials, int nparts, int C, float* sums, void* stream) {
+  USTRUN_REQUIRE(partials && sums && nparts > 0 && C > 0, "bn_reduce_partials: bad args");
+  k_bn_reduce_partials<<<ceil_div(2 * C, 128), 128, 0, (cudaStream_t)stream>>>(partials, nparts, C, sums);
+  return check_launch("bn_reduce_partials");
+}
+int ustrun_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
+                       const float* conv_bias, float* running_mean, float* running_var, long long* nbt, float momentum,
+                       float eps, int training, float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  USTRUN_REQUIRE(C > 0 && scale && shift && mean && rstd, "bn_finalize: bad args");
+  USTRUN_REQUIRE(!training || (partials && nparts > 0 && count > 0), "bn_finalize: training needs partials");
+  USTRUN_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval needs running stats");
+  k_bn_finalize<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, beta, conv_bias, running_mean,
+                                                                   running_var, nbt, momentum, eps, training, scale, shift, mean, rstd);
+  return check_launch("bn_finalize");
+}
+int ustrun_bn_act_fwd(const void* x, int ldx, const float* scale, const float* shift, int act, void* y, int ldy, void* pooled,
+                      int ldp, int dtype, int B, int H, int W, int C, void* stream) {
+  USTRUN_REQUIRE(x && y && scale && shift && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "bn_act_fwd: need C, ld %% 8 == 0");
+  long long npix = (long long)B * H * W;
+  if (pooled) {
+    USTRUN_REQUIRE(H % 2 == 0 && W % 2 == 0 && ldp % 8 == 0, "bn_act_fwd: pooling needs even H, W");
+    long long n = npix / 4 * (C / 8);
+    DISPATCH_DTYPE(dtype, (k_bn_act_pool<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, scale, shift, act, (T*)y,
+                                                                                               ldy, (T*)pooled, ldp, B, H, W, C)));
+  } else {
+    long long n = npix * (C / 8);
+    DISPATCH_DTYPE(dtype, (k_bn_act<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, scale, shift, act, (T*)y, ldy, npix, C)));
+  }
+  return check_launch("bn_act_fwd");
+}
+int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const float* mean, const float* rstd, const float* scale,
+                         const float* shift, int act, int dtype, long long npix, int C, float* partials, int* nparts_host, void* stream) {
+  USTRUN_REQUIRE(g && x && mean && rstd && scale && shift && partials && nparts_host, "bn_bwd_reduce: null arg");
+  USTRUN_REQUIRE(C % 8 == 0 && ldg % 8 == 0 && ldx % 8 == 0 && (C / 8) <= 256 && 256 % (C / 8) == 0, "bn_bwd_reduce: C=%d unsupported", C);
+  int lanes = 256 / (C / 8);
+  int grid = (int)((npix + lanes - 1) / lanes);
+  if (grid > USTRUN_MAX_PARTS) grid = USTRUN_MAX_PARTS;
+  if (grid > 148 * 4) grid = 148 * 4;
+  *nparts_host = grid;
+  DISPATCH_DTYPE(dtype, (k_bn_bwd_reduce<T><<<grid, 256, 256 * 16 * sizeof(float), (cudaStream_t)stream>>>(
+                            (const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale, shift, act, npix, C, partials)));
+  return check_launch("bn_bwd_reduce");
+}
+int ustrun_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* rstd, float* dgamma,
+                           float* dbeta, int accumulate, float* coef, void* stream) {
+  USTRUN_REQUIRE(partials && nparts > 0 && C > 0 && rstd && coef && count > 0, "bn_bwd_finalize: bad args");
+  k_bn_bwd_finalize<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, rstd, dgamma, dbeta, accumulate, coef);
+  return check_launch("bn_bwd_finalize");
+}
+int ustrun_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, const float* mean, const float* rstd, const float* scale,
+                        const float* shift, const float* coef, int act, void* dx, int lddx, int dtype, long long npix, int C, void* stream) {
+  USTRUN_REQUIRE(g && x && dx && coef && C % 8 == 0 && ldg % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: bad args");
+  long long n = npix * (C / 8);
+  DISPATCH_DTYPE(dtype, (k_bn_bwd_apply<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale,
+                                                                                              shift, coef, act, (T*)dx, lddx, npix, C)));
+  return check_launch("bn_bwd_apply");
+}
+int ustrun_maxpool_bwd(const void* y, int ldy, const void* dpool, int ldp, const void* gskip, int ldgs, void* gout, int ldgo, int dtype,
+                       int B, int H, int W, int C, void* stream) {
+  USTRUN_REQUIRE(y && dpool && gout && C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && ldy % 8 == 0 && ldp % 8 == 0 && ldgo % 8 == 0 &&
+                     (!gskip || ldgs % 8 == 0), "maxpool_bwd: bad args");
+  long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  DISPATCH_DTYPE(dtype, (k_maxpool_bwd<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y, ldy, (const T*)dpool, ldp, (const T*)gskip,
+                                                                                             ldgs, (T*)gout, ldgo, B, H, W, C)));
+  return check_launch("maxpool_bwd");
+}
+int ustrun_upsample2x_fwd(const void* x, int ldx, void* y, int ldy, int dtype, int B, int H, int W, int C, int align, void* stream) {
+  USTRUN_REQUIRE(x && y && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "upsample2x_fwd: bad args");
+  long long n = (long long)B * 4 * H * W * (C / 8);
+  DISPATCH_DTYPE(dtype, (k_upsample2x_fwd<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)y, ldy, B, H, W, C, align)));
+  return check_launch("upsample2x_fwd");
+}
+int ustrun_upsample2x_bwd(const void* dy, int lddy, void* dx, int lddx, int dtype, int B, int H, int W, int C, int align, void* stream) {
+  USTRUN_REQUIRE(dy && dx && C % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, "upsample2x_bwd: bad args");
+  long long n = (long long)B * H * W * (C / 8);
+  DISPATCH_DTYPE(dtype, (k_upsample2x_bwd<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, lddy, (T*)dx, lddx, B, H, W, C, align)));
+  return check_launch("upsample2x_bwd");
+}
+int ustrun_channel_sum(const void* x, int ldx, int dtype, long long npix, int C, float* out, int accumulate, float* workspace, void* stream) {
+  USTRUN_REQUIRE(x && out && workspace && npix > 0 && C > 0, "channel_sum: bad args");
+  int parts = (int)((npix + 63) / 64);
+  if (parts > USTRUN_MAX_PARTS) parts = USTRUN_MAX_PARTS;
+  dim3 grid(parts, ceil_div(C, 32)), block(32, 8);
+  DISPATCH_DTYPE(dtype, (k_channel_sum_partial<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, ldx, npix, C, workspace)));
+  k_channel_sum_final<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(workspace, parts, C, out, accumulate);
+  return check_launch("channel_sum");
+}
+
+}  // extern "C"

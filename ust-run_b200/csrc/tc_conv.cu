@@ -1,0 +1,719 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (bf16 in, fp32 accumulate).
+//
+//   k_tc_conv  : forward-type GEMM  D[pixel][cout] = sum_{tap,ci} X[pixel+tap][ci] * W[cout][tap][ci]
+//                (conv3x3 fwd, dgrad via flipped packing, conv1x1, the 4 GEMMs of ConvTranspose2d,
+//                 ConvTranspose2d dgrad).  A (activations) arrives as 4-D TMA boxes over the NHWC
+//                tensor -- one box of TH x TW pixels x 64 channels per (tap, channel chunk), halo and
+//                padding produced by TMA out-of-bounds zero fill -- B (weights, K-major) as 2-D
+//                boxes.  Both land in 128B-swizzled smem and feed tcgen05.mma (M=128, N=BN, K=16)
+//                accumulating in TMEM.  Persistent CTAs, 4..8-stage mbarrier ring, double-buffered
+//                accumulators; the epilogue warps read TMEM with tcgen05.ld, fuse bias and the
+//                per-channel BatchNorm statistics (sum, sum of squares of the fp32 accumulators,
+//                butterfly warp-shuffle reduction over the 32 pixel rows a warp owns), pack bf16
+//                into a swizzled staging tile and TMA-store it.
+//   k_tc_wgrad : weight gradient  D[co][ci] = sum_pixel dY[pixel][co] * X[pixel+tap][ci]; both
+//                operands are MN-major views of the same NHWC TMA boxes (K = pixels), split-K over
+//                CTAs with fp32 partials reduced by k_wgrad_reduce.
+//
+// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ustrun {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// descriptors (cute/arch/mma_sm100_desc.hpp bit layout)
+// ------------------------------------------------------------------------------------------
+// instruction descriptor: D=f32, A=B=bf16, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// lane j of the warp returns sum over the 32 lanes of v[j]  (31 shuffles for 32 columns)
+__device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      float send = hi ? v[i] : v[i + o];
+      float keep = hi ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// forward-type kernel
+// ------------------------------------------------------------------------------------------
+enum { TAP_CONV3 = 0, TAP_NONE = 1, TAP_PERMAP = 2 };
+
+struct TcConvParams {
+  int B, H, W;           // GEMM-row pixel grid
+  int Cin, Cout;
+  int ntaps, tap_mode;
+  int TW, TH, tiles_w, tiles_h;
+  int m_tiles, n_tiles, ctas_per_n;
+  float* partials;       // [ctas_per_n][2][Cout] or null
+  const float* bias;     // [Cout] or null
+};
+
+constexpr int kEpiBar0 = 1, kEpiBar1 = 2;
+constexpr uint32_t kStageA = 128 * 128;        // 128 pixel rows x 128 B
+constexpr uint32_t kStagingBytes = 2 * 16384;
+
+template <int BN> struct FwdCfg {
+  static constexpr uint32_t stageB = BN * 128;
+  static constexpr uint32_t stage = kStageA + stageB;
+  static constexpr int stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr uint32_t smem = stages * stage + kStagingBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+          const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
+          const TcConvParams p) {
+  using Cfg = FwdCfg<BN>;
+  constexpr int S = Cfg::stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* staging = smem + S * Cfg::stage;
+  uint64_t* full_bar = (uint64_t*)(staging + kStagingBytes);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_holder = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int cta_j = blockIdx.x / p.n_tiles;
+  const int n0 = n_tile * BN;
+  const int kchunks = p.Cin >> 6;
+  const int num_kb = p.ntaps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA0);
+    prefetch_tmap(&mapW);
+    prefetch_tmap(&mapO);
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n) {
+        const int txi = mt % p.tiles_w, tyi = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = txi * p.TW, h0 = tyi * p.TH;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          int dh = 0, dw = 0;
+          const CUtensorMap* mA = &mapA0;
+          if (p.tap_mode == TAP_CONV3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+          else if (p.tap_mode == TAP_PERMAP) mA = tap == 0 ? &mapA0 : (tap == 1 ? &mapA1 : (tap == 2 ? &mapA2 : &mapA3));
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::stage;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)(p.TH * p.TW * 128) + Cfg::stageB);
+            tma_load_4d(sa, mA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, b);
+            tma_load_2d(sa + kStageA, &mapW, &full_bar[stage], (tap * kchunks + kc) * 64, n0);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::stage);
+          const uint64_t adesc = make_sdesc(sa, 16, 1024);
+          const uint64_t bdesc = make_sdesc(sa + kStageA, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)     // 64 channels = 4 x UMMA_K(16); +32 B inside the swizzle row
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          tc_commit(&empty_bar[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;                     // TMEM lane quadrant
+    const int row = q * 32 + lane;              // pixel row inside the tile
+    const int epi_tid = threadIdx.x - 128;
+    float ssum[BN / 32], ssq[BN / 32];
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+    int it = 0;
+    uint32_t chunk_ctr = 0;
+    for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int txi = mt % p.tiles_w, tyi = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = txi * p.TW, h0 = tyi * p.TH;
+      const int th = row / p.TW, tw = row - th * p.TW;
+      const bool valid = (row < p.TH * p.TW) && (h0 + th < p.H) && (w0 + tw < p.W);
+      mbar_wait(&tfull_bar[buf], acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int c64 = 0; c64 < BN / 64; ++c64, ++chunk_ctr) {
+        uint8_t* stg = staging + (chunk_ctr & 1) * 16384;
+        if (epi_tid == 0) tma_store_wait_read<1>();    // the store that last used this buffer has drained
+        named_bar_sync(kEpiBar0, 128);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c32 = c64 * 2 + half;
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c32 * 32), v);
+          uint32_t packed[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = v[2 * i], c = v[2 * i + 1];
+            if (p.bias) { a += p.bias[n0 + c32 * 32 + 2 * i]; c += p.bias[n0 + c32 * 32 + 2 * i + 1]; }
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
+            packed[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                 // 4 x 16 B chunks of this half row, 128B swizzle
+            const int chunk = half * 4 + j;
+            uint4 val = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            *reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4)) = val;
+          }
+          if (p.partials) {
+            float sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
+            ssum[c32] += butterfly_colsum(v, lane);
+            ssq[c32] += butterfly_colsum(sq, lane);
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(kEpiBar1, 128);
+        if (epi_tid == 0) {
+          tma_store_4d(&mapO, stg, n0 + c64 * 64, w0, h0, b);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+    if (epi_tid == 0) tma_store_wait_all();
+    if (p.partials) {
+      named_bar_sync(kEpiBar0, 128);
+      float* red = reinterpret_cast<float*>(staging);   // [4 warps][2][BN]
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        red[(q * 2 + 0) * BN + i * 32 + lane] = ssum[i];
+        red[(q * 2 + 1) * BN + i * 32 + lane] = ssq[i];
+      }
+      named_bar_sync(kEpiBar1, 128);
+      for (int o = epi_tid; o < 2 * BN; o += 128) {
+        const int which = o / BN, c = o - which * BN;
+        float s = red[(0 * 2 + which) * BN + c] + red[(1 * 2 + which) * BN + c] + red[(2 * 2 + which) * BN + c] + red[(3 * 2 + which) * BN + c];
+        p.partials[(size_t)cta_j * 2 * p.Cout + (size_t)which * p.Cout + n0 + c] = s;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight-gradient kernel
+// ------------------------------------------------------------------------------------------
+struct TcWgradParams {
+  int B, H, W;             // pixel grid of the K loop
+  int Mo, Nin;             // GEMM M (<= channels of the A-side tensor) and N channels per tap
+  int ntaps, tap_mode;     // TAP_CONV3 shifts the N-side operand; TAP_PERMAP picks mapB[tap]
+  int TW, TH, tiles_w, tiles_h, pix_tiles;
+  int m_tiles, n_tiles, splits, tiles_per_split;
+  float* ws;               // [splits][Mo][ntaps*Nin]
+};
+
+template <int BN> struct WgCfg {
+  static constexpr uint32_t stageA = 2 * 64 * 128;            // two 64-channel atoms x 64 pixels
+  static constexpr uint32_t stageB = (BN / 64) * 64 * 128;
+  static constexpr uint32_t stage = stageA + stageB;
+  static constexpr int stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr uint32_t smem = stages * stage + 1024 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+k_tc_wgrad(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+           const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapB3, const TcWgradParams p) {
+  using Cfg = WgCfg<BN>;
+  constexpr int S = Cfg::stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + S * Cfg::stage);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint32_t* tmem_holder = (uint32_t*)(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item: tap fastest so the taps of one (tile, split) run concurrently and share L2 lines
+  int wi = blockIdx.x;
+  const int tap = wi % p.ntaps; wi /= p.ntaps;
+  const int n_tile = wi % p.n_tiles; wi /= p.n_tiles;
+  const int m_tile = wi % p.m_tiles; wi /= p.m_tiles;
+  const int split = wi;
+  const int pt_begin = split * p.tiles_per_split;
+  const int pt_end = min(pt_begin + p.tiles_per_split, p.pix_tiles);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB0);
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int dh = 0, dw = 0;
+      const CUtensorMap* mB = &mapB0;
+      if (p.tap_mode == TAP_CONV3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+      else if (p.tap_mode == TAP_PERMAP) mB = tap == 0 ? &mapB0 : (tap == 1 ? &mapB1 : (tap == 2 ? &mapB2 : &mapB3));
+      int stage = 0; uint32_t phase = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        const int txi = pt % p.tiles_w, tyi = (pt / p.tiles_w) % p.tiles_h, b = pt / (p.tiles_w * p.tiles_h);
+        const int w0 = txi * p.TW, h0 = tyi * p.TH;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::stage;
+        mbar_expect_tx(&full_bar[stage], Cfg::stage);
+        tma_load_4d(sa, &mapA, &full_bar[stage], m_tile * 128, w0, h0, b);
+        tma_load_4d(sa + 8192, &mapA, &full_bar[stage], m_tile * 128 + 64, w0, h0, b);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(sa + Cfg::stageA + j * 8192, mB, &full_bar[stage], n_tile * BN + j * 64, w0 + dw, h0 + dh, b);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::stage);
+        // MN-major, 128B swizzle: LBO = stride between 64-channel atoms (8 KB), SBO = 8 pixel rows (1 KB)
+        const uint64_t adesc = make_sdesc(sa, 8192, 1024);
+        const uint64_t bdesc = make_sdesc(sa + Cfg::stageA, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)       // 64 pixels = 4 x UMMA_K(16): advance 16 rows = 2 KB
+          tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (pt > pt_begin) || (k > 0));
+        tc_commit(&empty_bar[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int m = m_tile * 128 + q * 32 + lane;
+    const int N = p.ntaps * p.Nin;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c32 = 0; c32 < BN / 32; ++c32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c32 * 32), v);
+      const int c = n_tile * BN + c32 * 32;
+      if (m < p.Mo && c < p.Nin && pt_end > pt_begin) {
+        float* dst = p.ws + ((size_t)split * p.Mo + m) * N + (size_t)tap * p.Nin + c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps + launches
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)ptr;
+  }
+  return fn;
+}
+
+// 4-D NHWC bf16 view: dims (C, W, H, B) with element strides (1, sw, sh, sb); box (64, TW, TH, 1)
+static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int B, long long sw, long long sh, long long sb, int TW, int TH) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return USTRUN_ERR_ARG; }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t est[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act C=%d W=%d H=%d B=%d box %dx%d) failed: %d", C, W, H, B, TW, TH, (int)r); return USTRUN_ERR_ARG; }
+  return 0;
+}
+static int make_w_map(CUtensorMap* m, const void* base, long long K, int rows, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return USTRUN_ERR_ARG; }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t est[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights K=%lld rows=%d) failed: %d", K, rows, (int)r); return USTRUN_ERR_ARG; }
+  return 0;
+}
+
+// pick the TH x TW pixel box (TH*TW <= target) covering an H x W image with the least padding
+static void pick_tile(int H, int W, int target, bool exact_pow2, int& TW, int& TH) {
+  double best = -1.0;
+  TW = 1; TH = 1;
+  for (int tw = 1; tw <= W && tw <= target && tw <= 256; ++tw) {
+    if (exact_pow2 && (tw & (tw - 1))) continue;
+    int th = target / tw;
+    if (th > 256) th = 256;
+    if (th < 1) continue;
+    if (exact_pow2 && tw * th != target) continue;
+    if (!exact_pow2 && th > H) th = H;
+    long long cover = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+    double eff = (double)H * W / ((double)cover * target);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > TW)) { best = eff; TW = tw; TH = th; }
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+struct ActView {            // NHWC bf16 view in elements
+  const void* base;
+  int C, W, H, B;
+  long long sw, sh, sb;
+};
+
+template <int BN>
+static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot, const ActView& out, TcConvParams p, cudaStream_t st) {
+  using Cfg = FwdCfg<BN>;
+  CUtensorMap mA[4], mW, mO;
+  for (int i = 0; i < 4; ++i) {
+    const ActView& v = a[i < nmaps ? i : 0];
+    int rc = make_act_map(&mA[i], v.base, v.C, v.W, v.H, v.B, v.sw, v.sh, v.sb, p.TW, p.TH);
+    if (rc) return rc;
+  }
+  int rc = make_w_map(&mW, w, Ktot, p.Cout, BN);
+  if (rc) return rc;
+  rc = make_act_map(&mO, out.base, out.C, out.W, out.H, out.B, out.sw, out.sh, out.sb, p.TW, p.TH);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_tc_conv<%d>, %u): %s", BN, Cfg::smem, cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  p.n_tiles = p.Cout / BN;
+  int per = num_sms() / p.n_tiles;
+  if (per < 1) per = 1;
+  if (per > p.m_tiles) per = p.m_tiles;
+  if (per > USTRUN_MAX_PARTS) per = USTRUN_MAX_PARTS;
+  p.ctas_per_n = per;
+  k_tc_conv<BN><<<p.n_tiles * per, 256, Cfg::smem, st>>>(mA[0], mA[1], mA[2], mA[3], mW, mO, p);
+  return check_launch("k_tc_conv");
+}
+
+// x: [B,H,W,Cin] (ldx), y: [B,H,W,Cout] (ldy); generic entry used by conv3x3/1x1 fwd+dgrad
+int tc_conv_fwd(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize,
+                float* partials, int* nparts_host, cudaStream_t st) {
+  if (Cin % 64 || Cout % 64 || ldx % 8 || ldy % 8) { set_error("tcgen05 conv needs Cin, Cout %% 64 == 0 (got %d, %d)", Cin, Cout); return USTRUN_ERR_ARG; }
+  TcConvParams p{};
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.ntaps = ksize * ksize; p.tap_mode = ksize == 3 ? TAP_CONV3 : TAP_NONE;
+  pick_tile(H, W, 128, false, p.TW, p.TH);
+  p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
+  p.m_tiles = B * p.tiles_w * p.tiles_h;
+  p.partials = partials; p.bias = bias;
+  ActView a{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
+  ActView o{y, Cout, W, H, B, ldy, (long long)W * ldy, (long long)H * W * ldy};
+  const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  int nt = Cout / BN, per = num_sms() / nt;
+  if (per < 1) per = 1;
+  if (per > p.m_tiles) per = p.m_tiles;
+  if (per > USTRUN_MAX_PARTS) per = USTRUN_MAX_PARTS;
+  if (nparts_host) *nparts_host = per;
+  long long Ktot = (long long)p.ntaps * Cin;
+  if (BN == 256) return launch_fwd<256>(&a, 1, w, Ktot, o, p, st);
+  if (BN == 128) return launch_fwd<128>(&a, 1, w, Ktot, o, p, st);
+  return launch_fwd<64>(&a, 1, w, Ktot, o, p, st);
+}
+
+// ConvTranspose2d(k2,s2) forward: four 1x1 GEMMs, each TMA-storing into the (2h+i, 2w+j) sub-grid
+int tc_convT_fwd(const void* x, int ldx, const void* wf, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout,
+                 cudaStream_t st) {
+  if (Cin % 64 || Cout % 64 || ldx % 8 || ldy % 8) { set_error("tcgen05 convT needs Cin, Cout %% 64 == 0"); return USTRUN_ERR_ARG; }
+  for (int ij = 0; ij < 4; ++ij) {
+    TcConvParams p{};
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ntaps = 1; p.tap_mode = TAP_NONE;
+    pick_tile(H, W, 128, false, p.TW, p.TH);
+    p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
+    p.m_tiles = B * p.tiles_w * p.tiles_h;
+    p.partials = nullptr; p.bias = bias;
+    ActView a{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
+    const char* ybase = (const char*)y + ((long long)(ij >> 1) * 2 * W + (ij & 1)) * ldy * 2;
+    ActView o{ybase, Cout, W, H, B, 2LL * ldy, 4LL * W * ldy, 4LL * H * W * ldy};
+    const char* wij = (const char*)wf + (size_t)ij * Cout * Cin * 2;
+    const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    int rc = BN == 256 ? launch_fwd<256>(&a, 1, wij, Cin, o, p, st) : (BN == 128 ? launch_fwd<128>(&a, 1, wij, Cin, o, p, st) : launch_fwd<64>(&a, 1, wij, Cin, o, p, st));
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// ConvTranspose2d dgrad: dx[b,h,w,ci] = sum_{ij,co} dy[b,2h+i,2w+j,co] * wd[ci][ij][co]
+int tc_convT_dgrad(const void* dy, int lddy, const void* wd, void* dx, int lddx, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  if (Cin % 64 || Cout % 64 || lddy % 8 || lddx % 8) { set_error("tcgen05 convT dgrad needs Cin, Cout %% 64 == 0"); return USTRUN_ERR_ARG; }
+  TcConvParams p{};
+  p.B = B; p.H = H; p.W = W; p.Cin = Cout; p.Cout = Cin; p.ntaps = 4; p.tap_mode = TAP_PERMAP;
+  pick_tile(H, W, 128, false, p.TW, p.TH);
+  p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
+  p.m_tiles = B * p.tiles_w * p.tiles_h;
+  ActView a[4];
+  for (int ij = 0; ij < 4; ++ij) {
+    const char* base = (const char*)dy + ((long long)(ij >> 1) * 2 * W + (ij & 1)) * lddy * 2;
+    a[ij] = ActView{base, Cout, W, H, B, 2LL * lddy, 4LL * W * lddy, 4LL * H * W * lddy};
+  }
+  ActView o{dx, Cin, W, H, B, lddx, (long long)W * lddx, (long long)H * W * lddx};
+  const int BN = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
+  long long Ktot = 4LL * Cout;
+  if (BN == 256) return launch_fwd<256>(a, 4, wd, Ktot, o, p, st);
+  if (BN == 128) return launch_fwd<128>(a, 4, wd, Ktot, o, p, st);
+  return launch_fwd<64>(a, 4, wd, Ktot, o, p, st);
+}
+
+int launch_wgrad_reduce(const float* ws, int splits, int Mo, int Nin, int taps, float* dw, int accumulate, cudaStream_t st);
+
+struct WgPlan { int TW, TH, tiles_w, tiles_h, pix_tiles, m_tiles, n_tiles, BN, splits, tps; };
+static WgPlan plan_wgrad(int B, int H, int W, int Mo, int Nin, int ntaps) {
+  WgPlan g;
+  pick_tile(H, W, 64, true, g.TW, g.TH);
+  g.tiles_w = (W + g.TW - 1) / g.TW; g.tiles_h = (H + g.TH - 1) / g.TH;
+  g.pix_tiles = B * g.tiles_w * g.tiles_h;
+  g.BN = Nin % 256 == 0 ? 256 : (Nin % 128 == 0 ? 128 : 64);
+  g.m_tiles = (Mo + 127) / 128; g.n_tiles = Nin / g.BN;
+  long long items = (long long)ntaps * g.m_tiles * g.n_tiles;
+  long long want = (2LL * num_sms() + items - 1) / items;       // ~2 waves of CTAs
+  if (want < 1) want = 1;
+  long long maxs = (g.pix_tiles + 7) / 8;                       // >= 8 pixel tiles (512 pixels) per split
+  if (maxs < 1) maxs = 1;
+  if (want > maxs) want = maxs;
+  g.tps = (int)((g.pix_tiles + want - 1) / want);
+  g.splits = (g.pix_tiles + g.tps - 1) / g.tps;
+  return g;
+}
+long long tc_wgrad_ws_bytes(int B, int H, int W, int Mo, int Nin, int ntaps) {
+  WgPlan g = plan_wgrad(B, H, W, Mo, Nin, ntaps);
+  return (long long)g.splits * Mo * ntaps * Nin * (long long)sizeof(float);
+}
+
+template <int BN>
+static int launch_wgrad(const ActView& a, const ActView* bviews, int nb, TcWgradParams p, cudaStream_t st) {
+  using Cfg = WgCfg<BN>;
+  CUtensorMap mA, mB[4];
+  int rc = make_act_map(&mA, a.base, a.C, a.W, a.H, a.B, a.sw, a.sh, a.sb, p.TW, p.TH);
+  if (rc) return rc;
+  for (int i = 0; i < 4; ++i) {
+    const ActView& v = bviews[i < nb ? i : 0];
+    rc = make_act_map(&mB[i], v.base, v.C, v.W, v.H, v.B, v.sw, v.sh, v.sb, p.TW, p.TH);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_tc_wgrad<%d>): %s", BN, cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  int grid = p.ntaps * p.m_tiles * p.n_tiles * p.splits;
+  k_tc_wgrad<BN><<<grid, 256, Cfg::smem, st>>>(mA, mB[0], mB[1], mB[2], mB[3], p);
+  return check_launch("k_tc_wgrad");
+}
+
+// generic: A-side tensor (M channels, unshifted), B-side tensor(s) (N channels per tap)
+static int tc_wgrad_generic(const ActView& a, const ActView* bviews, int nb, int tap_mode, int ntaps, int B, int H, int W, int Mo, int Nin,
+                            float* dw, int accumulate, void* workspace, long long ws_bytes, cudaStream_t st) {
+  WgPlan g = plan_wgrad(B, H, W, Mo, Nin, ntaps);
+  long long need = (long long)g.splits * Mo * ntaps * Nin * (long long)sizeof(float);
+  if (!workspace || ws_bytes < need) { set_error("tc wgrad: workspace too small (%lld < %lld)", ws_bytes, need); return USTRUN_ERR_ARG; }
+  TcWgradParams p{};
+  p.B = B; p.H = H; p.W = W; p.Mo = Mo; p.Nin = Nin; p.ntaps = ntaps; p.tap_mode = tap_mode;
+  p.TW = g.TW; p.TH = g.TH; p.tiles_w = g.tiles_w; p.tiles_h = g.tiles_h; p.pix_tiles = g.pix_tiles;
+  p.m_tiles = g.m_tiles; p.n_tiles = g.n_tiles; p.splits = g.splits; p.tiles_per_split = g.tps;
+  p.ws = (float*)workspace;
+  int rc = g.BN == 256 ? launch_wgrad<256>(a, bviews, nb, p, st) : (g.BN == 128 ? launch_wgrad<128>(a, bviews, nb, p, st) : launch_wgrad<64>(a, bviews, nb, p, st));
+  if (rc) return rc;
+  return launch_wgrad_reduce((const float*)workspace, g.splits, Mo, Nin, ntaps, dw, accumulate, st);
+}
+
+int tc_conv_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout, int ksize,
+                  void* workspace, long long ws_bytes, cudaStream_t st) {
+  if (Cin % 64 || Cout % 64 || lddy % 8 || ldx % 8) { set_error("tcgen05 wgrad needs Cin, Cout %% 64 == 0"); return USTRUN_ERR_ARG; }
+  ActView a{dy, Cout, W, H, B, lddy, (long long)W * lddy, (long long)H * W * lddy};
+  ActView b{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
+  return tc_wgrad_generic(a, &b, 1, ksize == 3 ? TAP_CONV3 : TAP_NONE, ksize * ksize, B, H, W, Cout, Cin, dw, accumulate, workspace, ws_bytes, st);
+}
+long long tc_conv_wgrad_ws(int B, int H, int W, int Cin, int Cout, int ksize) { return tc_wgrad_ws_bytes(B, H, W, Cout, Cin, ksize * ksize); }
+
+// dW[ci][co][ij] = sum_p x[p][ci] * dy[b,2h+i,2w+j][co]
+int tc_convT_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout,
+                   void* workspace, long long ws_bytes, cudaStream_t st) {
+  if (Cin % 64 || Cout % 64 || lddy % 8 || ldx % 8) { set_error("tcgen05 convT wgrad needs Cin, Cout %% 64 == 0"); return USTRUN_ERR_ARG; }
+  ActView a{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
+  ActView bv[4];
+  for (int ij = 0; ij < 4; ++ij) {
+    const char* base = (const char*)dy + ((long long)(ij >> 1) * 2 * W + (ij & 1)) * lddy * 2;
+    bv[ij] = ActView{base, Cout, W, H, B, 2LL * lddy, 4LL * W * lddy, 4LL * H * W * lddy};
+  }
+  return tc_wgrad_generic(a, bv, 4, TAP_PERMAP, 4, B, H, W, Cin, Cout, dw, accumulate, workspace, ws_bytes, st);
+}
+long long tc_convT_wgrad_ws(int B, int H, int W, int Cin, int Cout) { return tc_wgrad_ws_bytes(B, H, W, Cin, Cout, 4); }
+
+}  // namespace ustrun

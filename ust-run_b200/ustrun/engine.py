@@ -1,0 +1,489 @@
+"""Host-side execution engine: NHWC activations, layer ops and a layer-level backward tape.
+
+The nn.Module drop-ins (networks/*.py) describe a network as a sequence of these ops; every op
+launches kernels of libustrun_sm100.so through the C ABI (``_lib.call``) on torch's current CUDA
+stream.  PyTorch is used for memory (torch.empty), streams and parameter storage only.
+
+Precision modes (``set_precision``):
+  * ``"bf16"`` (default): bf16 NHWC activations, fp32 accumulation; convs with Cin,Cout % 64 == 0
+    run on the tcgen05 kernels, the narrow ones (first conv, logits head, 16/32-channel UNet-B
+    levels) on the CUDA-core kernels.
+  * ``"fp32"``: validation mode, everything fp32 on the CUDA-core kernels (1e-4 parity target).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+
+_PRECISION = os.environ.get("USTRUN_PRECISION", "bf16")
+_FORCE_SIMT = os.environ.get("USTRUN_FORCE_SIMT", "0") == "1"
+LAUNCHES = 0          # kernels-launching C calls issued (bench.py reports it)
+
+
+def set_precision(mode: str) -> None:
+    global _PRECISION
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def set_force_simt(flag: bool) -> None:
+    global _FORCE_SIMT
+    _FORCE_SIMT = bool(flag)
+
+
+def _dt():
+    return (torch.bfloat16, L.BF16) if _PRECISION == "bf16" else (torch.float32, L.F32)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    L.call(name, *args)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Act:
+    """An NHWC activation: ``t`` is a contiguous [B,H,W,ld] tensor, the activation is channels
+    [c0, c0+C) of it (so an Act may be one half of a concat buffer)."""
+
+    __slots__ = ("t", "B", "H", "W", "C", "c0", "parent", "_g", "needs_grad")
+
+    def __init__(self, t, C=None, c0=0, parent=None):
+        self.t = t
+        self.B, self.H, self.W = t.shape[0], t.shape[1], t.shape[2]
+        self.C = t.shape[3] if C is None else C
+        self.c0 = c0
+        self.parent = parent
+        self._g = None
+        self.needs_grad = False
+
+    @staticmethod
+    def new(B, H, W, C, dtype=None, device=None):
+        return Act(torch.empty((B, H, W, C), dtype=dtype or _dt()[0], device=device or "cuda"))
+
+    def like(self, C=None):
+        return Act(torch.empty((self.B, self.H, self.W, C or self.C), dtype=self.t.dtype, device=self.t.device))
+
+    def view(self, c0, C):
+        return Act(self.t, C, self.c0 + c0, parent=self)
+
+    @property
+    def ld(self):
+        return self.t.shape[3]
+
+    @property
+    def npix(self):
+        return self.B * self.H * self.W
+
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.t.data_ptr() + self.c0 * self.t.element_size())
+
+    @property
+    def dtype_code(self):
+        return L.BF16 if self.t.dtype == torch.bfloat16 else L.F32
+
+    # gradient buffer: views resolve through their parent (concat halves)
+    @property
+    def g(self):
+        if self.parent is not None:
+            pg = self.parent.g
+            return None if pg is None else Act(pg.t, self.C, pg.c0 + (self.c0 - self.parent.c0), parent=None)
+        return self._g
+
+    @g.setter
+    def g(self, value):
+        if self.parent is not None:
+            raise RuntimeError("cannot assign the gradient of a view")
+        self._g = value
+
+
+class GradSink:
+    """Where weight gradients go.  ``get(param)`` returns (fp32 tensor, accumulate_flag)."""
+
+    def __init__(self, provider: Optional[Callable] = None):
+        self.provider = provider
+        self.fresh: Dict[int, torch.Tensor] = {}
+
+    def get(self, param: torch.Tensor):
+        if self.provider is not None:
+            return self.provider(param), 1
+        key = id(param)
+        if key in self.fresh:
+            return self.fresh[key], 1
+        g = torch.empty_like(param, dtype=torch.float32)
+        self.fresh[key] = g
+        return g, 0
+
+
+class Ctx:
+    """One forward pass: holds the backward tape when gradients are needed."""
+
+    def __init__(self, training: bool, need_grad: bool, bn_sync: Optional[Callable] = None):
+        self.training = training
+        self.need_grad = need_grad
+        self.tape: List[Callable] = []
+        self.bn_sync = bn_sync           # callable(tensor[2*C]) -> None (in-place cross-rank sum) or None
+        self.bn_world = 1
+
+    def backward(self, sink: GradSink):
+        for fn in reversed(self.tape):
+            fn(sink)
+        self.tape = []
+
+
+# --------------------------------------------------------------------------------------------
+# packed weights (bf16/fp32 [Cout][tap][Cin] forward and [Cin][tap'][Cout] dgrad copies)
+# --------------------------------------------------------------------------------------------
+class PackedConv:
+    def __init__(self):
+        self.key = None
+        self.wf = None
+        self.wd = None
+
+    def get(self, weight: torch.Tensor, transposed=False):
+        tdt, code = _dt()
+        key = (weight.data_ptr(), weight._version, code, getattr(weight, "_ustrun_epoch", 0))
+        if key != self.key:
+            w = weight.detach()
+            if w.dtype != torch.float32 or not w.is_contiguous():
+                w = w.float().contiguous()
+            if transposed:
+                cin, cout = w.shape[0], w.shape[1]
+                self.wf = torch.empty((4, cout, cin), dtype=tdt, device=w.device)
+                self.wd = torch.empty((cin, 4, cout), dtype=tdt, device=w.device)
+                _call("ustrun_pack_convT_weight", _ptr(w), _ptr(self.wf), _ptr(self.wd), code, cin, cout, _stream())
+            else:
+                cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+                self.wf = torch.empty((cout, k * k, cin), dtype=tdt, device=w.device)
+                self.wd = torch.empty((cin, k * k, cout), dtype=tdt, device=w.device)
+                _call("ustrun_pack_conv_weight", _ptr(w), _ptr(self.wf), _ptr(self.wd), code, cout, cin, k, _stream())
+            self.key = key
+        return self.wf, self.wd
+
+
+def mark_params_updated(params):
+    """Call after a kernel modified parameters through raw pointers (fused SGD/EMA)."""
+    for p in params:
+        p._ustrun_epoch = getattr(p, "_ustrun_epoch", 0) + 1
+
+
+def _impl_for(cin, cout, dtype_code):
+    if dtype_code == L.BF16 and not _FORCE_SIMT and cin % 64 == 0 and cout % 64 == 0:
+        return L.TCGEN05
+    return L.SIMT
+
+
+def _f32(t):
+    return t if t.dtype == torch.float32 else t.float()
+
+
+# --------------------------------------------------------------------------------------------
+# ops
+# --------------------------------------------------------------------------------------------
+def input_nchw(x: torch.Tensor) -> Act:
+    """NCHW fp32 module input -> NHWC activation (custom_transforms.py:739-747 produces NCHW)."""
+    if x.dim() != 4:
+        raise ValueError("expected 4D input (got {}D input)".format(x.dim()))
+    L.require_device()
+    x = _f32(x).contiguous()
+    B, C, H, W = x.shape
+    a = Act.new(B, H, W, C, device=x.device)
+    _call("ustrun_nchw_to_nhwc", _ptr(x), a.ptr, a.dtype_code, B, C, H, W, a.ld, _stream())
+    return a
+
+
+def to_nchw(a: Act) -> torch.Tensor:
+    out = torch.empty((a.B, a.C, a.H, a.W), dtype=torch.float32, device=a.t.device)
+    _call("ustrun_nhwc_to_nchw", a.ptr, a.dtype_code, a.ld, _ptr(out), a.B, a.C, a.H, a.W, _stream())
+    return out
+
+
+def _raw_conv(x: Act, wpk, bias, y: Act, ks, partials=None, out_nchw=None):
+    nparts = ctypes.c_int(0)
+    impl = L.SIMT if out_nchw is not None else _impl_for(x.C, y.C if y is not None else 0, x.dtype_code)
+    cout = out_nchw.shape[1] if out_nchw is not None else y.C
+    _call("ustrun_conv_fwd", impl, x.ptr, x.ld, _ptr(wpk), _ptr(bias), _ptr(out_nchw) if out_nchw is not None else y.ptr,
+          0 if out_nchw is not None else y.ld, x.dtype_code, x.B, x.H, x.W, x.C, cout, ks, 1 if out_nchw is not None else 0,
+          _ptr(partials), ctypes.byref(nparts), _stream())
+    return nparts.value
+
+
+def _wgrad(dy: Act, x: Act, dw: torch.Tensor, accumulate: int, ks: int):
+    impl = _impl_for(x.C, dy.C, x.dtype_code)
+    nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(impl, x.B, x.H, x.W, x.C, dy.C, ks)
+    ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.t.device)
+    _call("ustrun_conv_wgrad", impl, dy.ptr, dy.ld, x.ptr, x.ld, _ptr(dw), accumulate, x.dtype_code, x.B, x.H, x.W, x.C, dy.C, ks,
+          _ptr(ws), int(nbytes), _stream())
+
+
+class BNState:
+    """The tensors of one nn.BatchNorm2d (weight, bias, running_mean, running_var, num_batches_tracked)."""
+
+    def __init__(self, bn):
+        self.bn = bn
+
+    @property
+    def eps(self):
+        return float(self.bn.eps)
+
+    @property
+    def momentum(self):
+        return 0.1 if self.bn.momentum is None else float(self.bn.momentum)
+
+
+def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None, pool: bool = False, packed: PackedConv = None):
+    """conv(k=1|3, pad=k//2) -> BatchNorm2d (train: batch stats, eval: running stats) -> activation
+    [-> MaxPool2d(2)].  Returns (y, pooled|None).  ``out`` lets the result land in a concat buffer.
+    Reference: unet_parts.py:15-21,34 / unet.py:52-72,96-117."""
+    ks = conv.kernel_size[0]
+    cout = conv.out_channels
+    wf, wd = packed.get(conv.weight)
+    dev = x.t.device
+    raw = x.like(cout)
+    training = ctx.training and bn.training if hasattr(bn, "training") else ctx.training
+    use_batch_stats = training or (bn.running_mean is None)
+    partials = torch.empty(L.MAX_PARTS * 2 * cout, dtype=torch.float32, device=dev) if use_batch_stats else None
+    nparts = _raw_conv(x, wf, None, raw, ks, partials)
+    stats = torch.empty(4 * cout, dtype=torch.float32, device=dev)      # scale, shift, mean, rstd
+    scale, shift, mean, rstd = stats[:cout], stats[cout:2 * cout], stats[2 * cout:3 * cout], stats[3 * cout:]
+    count = float(x.npix)
+    if use_batch_stats and ctx.bn_sync is not None:
+        sums = torch.empty(2 * cout, dtype=torch.float32, device=dev)
+        _call("ustrun_bn_reduce_partials", _ptr(partials), nparts, cout, _ptr(sums), _stream())
+        ctx.bn_sync(sums)
+        partials, nparts, count = sums, 1, count * ctx.bn_world
+    track = bn.track_running_stats and bn.running_mean is not None and training
+    _call("ustrun_bn_finalize", _ptr(partials), nparts, cout, count, _ptr(bn.weight), _ptr(bn.bias), _ptr(conv.bias),
+          _ptr(bn.running_mean) if (track or not use_batch_stats) else None,
+          _ptr(bn.running_var) if (track or not use_batch_stats) else None,
+          _ptr(bn.num_batches_tracked) if track else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
+          1 if use_batch_stats else 0, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _stream())
+    y = out if out is not None else x.like(cout)
+    pooled = Act.new(x.B, x.H // 2, x.W // 2, cout, dtype=x.t.dtype, device=dev) if pool else None
+    _call("ustrun_bn_act_fwd", raw.ptr, raw.ld, _ptr(scale), _ptr(shift), act, y.ptr, y.ld, pooled.ptr if pool else None,
+          pooled.ld if pool else 0, x.dtype_code, x.B, x.H, x.W, cout, _stream())
+
+    if ctx.need_grad:
+        if not use_batch_stats:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not part of the SSL step")
+        world = ctx.bn_world if ctx.bn_sync is not None else 1
+        bn_sync = ctx.bn_sync
+
+        def bwd(sink: GradSink):
+            G = y.g
+            if pool and pooled.g is not None:
+                Gn = y.like() if y.parent is None else Act.new(y.B, y.H, y.W, y.C, dtype=y.t.dtype, device=dev)
+                _call("ustrun_maxpool_bwd", y.ptr, y.ld, pooled.g.ptr, pooled.g.ld, G.ptr if G is not None else None,
+                      G.ld if G is not None else 0, Gn.ptr, Gn.ld, y.dtype_code, y.B, y.H, y.W, y.C, _stream())
+                G = Gn
+            if G is None:
+                return
+            part = torch.empty(L.MAX_PARTS * 2 * cout, dtype=torch.float32, device=dev)
+            np_ = ctypes.c_int(0)
+            _call("ustrun_bn_bwd_reduce", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), act,
+                  raw.dtype_code, raw.npix, cout, _ptr(part), ctypes.byref(np_), _stream())
+            n_parts, cnt = np_.value, float(raw.npix)
+            if bn_sync is not None:
+                sums = torch.empty(2 * cout, dtype=torch.float32, device=dev)
+                _call("ustrun_bn_reduce_partials", _ptr(part), n_parts, cout, _ptr(sums), _stream())
+                bn_sync(sums)
+                part, n_parts, cnt = sums, 1, cnt * world
+            coef = torch.empty(3 * cout, dtype=torch.float32, device=dev)
+            dg, acc_g = sink.get(bn.weight) if bn.weight is not None else (None, 0)
+            db, acc_b = sink.get(bn.bias) if bn.bias is not None else (None, 0)
+            _call("ustrun_bn_bwd_finalize", _ptr(part), n_parts, cout, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
+                  1 if (acc_g or acc_b) else 0, _ptr(coef), _stream())
+            draw = raw.like()
+            _call("ustrun_bn_bwd_apply", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
+                  act, draw.ptr, draw.ld, raw.dtype_code, raw.npix, cout, _stream())
+            dw, acc_w = sink.get(conv.weight)
+            _wgrad(draw, x, dw, acc_w, ks)
+            if conv.bias is not None:
+                dbias, acc = sink.get(conv.bias)          # BN removes the mean: d/dbias == 0 exactly
+                if not acc:
+                    dbias.zero_()
+            if x.needs_grad:
+                gx = Act.new(x.B, x.H, x.W, x.C, dtype=x.t.dtype, device=dev)
+                _raw_conv(draw, wd, None, gx, ks)
+                _assign_grad(x, gx)
+
+        ctx.tape.append(bwd)
+        y.needs_grad = True
+        if pooled is not None:
+            pooled.needs_grad = True
+    return y, pooled
+
+
+def _assign_grad(x: Act, gx: Act):
+    if x.parent is not None:
+        raise RuntimeError("gradient of a view must come from its parent buffer")
+    x.g = gx
+
+
+def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
+    """nn.ConvTranspose2d(k2, s2) + bias, written straight into ``out`` (usually the second half
+    of the decoder's concat buffer): unet_parts.py:53,57,62-67."""
+    wf, wd = packed.get(up.weight, transposed=True)
+    cin, cout = up.in_channels, up.out_channels
+    impl = _impl_for(cin, cout, x.dtype_code)
+    _call("ustrun_convT2x2_fwd", impl, x.ptr, x.ld, _ptr(wf), _ptr(up.bias), out.ptr, out.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream())
+    if ctx.need_grad:
+        dev = x.t.device
+
+        def bwd(sink: GradSink):
+            G = out.g
+            if G is None:
+                return
+            dw, acc = sink.get(up.weight)
+            nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(impl, x.B, x.H, x.W, cin, cout, 2)
+            ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+            _call("ustrun_convT2x2_wgrad", impl, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code, x.B, x.H, x.W, cin, cout,
+                  _ptr(ws), int(nbytes), _stream())
+            if up.bias is not None:
+                db, accb = sink.get(up.bias)
+                wsb = torch.empty(L.MAX_PARTS * cout, dtype=torch.float32, device=dev)
+                _call("ustrun_channel_sum", G.ptr, G.ld, G.dtype_code, G.npix, cout, _ptr(db), accb, _ptr(wsb), _stream())
+            if x.needs_grad:
+                gx = Act.new(x.B, x.H, x.W, x.C, dtype=x.t.dtype, device=dev)
+                _call("ustrun_convT2x2_dgrad", impl, G.ptr, G.ld, _ptr(wd), gx.ptr, gx.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream())
+                _assign_grad(x, gx)
+
+        ctx.tape.append(bwd)
+        out.needs_grad = True
+    return out
+
+
+def upsample2x(ctx: Ctx, x: Act, align_corners: bool, out: Optional[Act] = None):
+    """nn.Upsample(scale_factor=2, mode='bilinear'): unet.py:84,127 / unet_parts.py:50."""
+    y = out if out is not None else Act.new(x.B, 2 * x.H, 2 * x.W, x.C, dtype=x.t.dtype, device=x.t.device)
+    _call("ustrun_upsample2x_fwd", x.ptr, x.ld, y.ptr, y.ld, x.dtype_code, x.B, x.H, x.W, x.C, 1 if align_corners else 0, _stream())
+    if ctx.need_grad:
+        def bwd(sink: GradSink):
+            G = y.g
+            if G is None or not x.needs_grad:
+                return
+            gx = Act.new(x.B, x.H, x.W, x.C, dtype=x.t.dtype, device=x.t.device)
+            _call("ustrun_upsample2x_bwd", G.ptr, G.ld, gx.ptr, gx.ld, x.dtype_code, x.B, x.H, x.W, x.C, 1 if align_corners else 0, _stream())
+            _assign_grad(x, gx)
+
+        ctx.tape.append(bwd)
+        y.needs_grad = x.needs_grad
+    return y
+
+
+def head_conv(ctx: Ctx, x: Act, conv, packed: PackedConv):
+    """Logits head (OutConv 1x1: unet_parts.py:74; out1/seg1 3x3: unet.py:182,312): fp32 NCHW out.
+    Returns (logits, backward_fn(dlogits, sink))."""
+    ks = conv.kernel_size[0]
+    cout = conv.out_channels
+    wf, wd = packed.get(conv.weight)
+    logits = torch.empty((x.B, cout, x.H, x.W), dtype=torch.float32, device=x.t.device)
+    _raw_conv(x, wf, conv.bias, None, ks, out_nchw=logits)
+
+    def bwd(dlogits: torch.Tensor, sink: GradSink):
+        dev = x.t.device
+        dlogits = _f32(dlogits).contiguous()
+        cpad = cout                                        # narrow NHWC copy of dlogits
+        G = Act.new(x.B, x.H, x.W, cpad, dtype=x.t.dtype, device=dev)
+        _call("ustrun_nchw_to_nhwc", _ptr(dlogits), G.ptr, G.dtype_code, x.B, cout, x.H, x.W, G.ld, _stream())
+        dw, acc = sink.get(conv.weight)
+        nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(L.SIMT, x.B, x.H, x.W, x.C, cout, ks)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+        _call("ustrun_conv_wgrad", L.SIMT, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code, x.B, x.H, x.W, x.C, cout, ks,
+              _ptr(ws), int(nbytes), _stream())
+        if conv.bias is not None:
+            db, accb = sink.get(conv.bias)
+            wsb = torch.empty(L.MAX_PARTS * cout, dtype=torch.float32, device=dev)
+            _call("ustrun_channel_sum", G.ptr, G.ld, G.dtype_code, G.npix, cout, _ptr(db), accb, _ptr(wsb), _stream())
+        if x.needs_grad:
+            gx = Act.new(x.B, x.H, x.W, x.C, dtype=x.t.dtype, device=dev)
+            nparts = ctypes.c_int(0)
+            _call("ustrun_conv_fwd", L.SIMT, G.ptr, G.ld, _ptr(wd), None, gx.ptr, gx.ld, x.dtype_code, x.B, x.H, x.W, cout, x.C, ks, 0,
+                  None, ctypes.byref(nparts), _stream())
+            _assign_grad(x, gx)
+
+    return logits, bwd
+
+
+def batchnorm_only(ctx: Ctx, x: Act, bn):
+    """Stand-alone BatchNorm2d on an activation (used by DomainSpecificBatchNorm2d.forward when the
+    module is called directly: dsbn.py:24-27).  Statistics come from the two-stage reduction kernel
+    (bn_bwd_reduce with g=x, mean=0, rstd=1 computes sum x and sum x*x), then finalize + apply."""
+    C, dev = x.C, x.t.device
+    training = ctx.training
+    use_batch = training or bn.running_mean is None
+    stats = torch.empty(4 * C, dtype=torch.float32, device=dev)
+    scale, shift, mean, rstd = stats[:C], stats[C:2 * C], stats[2 * C:3 * C], stats[3 * C:]
+    part, nparts = None, 0
+    if use_batch:
+        ident = torch.empty(3 * C, dtype=torch.float32, device=dev)
+        ident[:C] = 0.0
+        ident[C:] = 1.0
+        zero, one = ident[:C], ident[C:2 * C]
+        part = torch.empty(L.MAX_PARTS * 2 * C, dtype=torch.float32, device=dev)
+        np_ = ctypes.c_int(0)
+        _call("ustrun_bn_bwd_reduce", x.ptr, x.ld, x.ptr, x.ld, _ptr(zero), _ptr(one), _ptr(one), _ptr(zero), L.ACT_NONE, x.dtype_code,
+              x.npix, C, _ptr(part), ctypes.byref(np_), _stream())
+        nparts = np_.value
+    count = float(x.npix)
+    if use_batch and ctx.bn_sync is not None:
+        sums = torch.empty(2 * C, dtype=torch.float32, device=dev)
+        _call("ustrun_bn_reduce_partials", _ptr(part), nparts, C, _ptr(sums), _stream())
+        ctx.bn_sync(sums)
+        part, nparts, count = sums, 1, count * ctx.bn_world
+    track = bn.track_running_stats and bn.running_mean is not None and training
+    _call("ustrun_bn_finalize", _ptr(part), nparts, C, count, _ptr(bn.weight), _ptr(bn.bias), None,
+          _ptr(bn.running_mean) if (track or not use_batch) else None, _ptr(bn.running_var) if (track or not use_batch) else None,
+          _ptr(bn.num_batches_tracked) if track else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
+          1 if use_batch else 0, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _stream())
+    y = x.like()
+    _call("ustrun_bn_act_fwd", x.ptr, x.ld, _ptr(scale), _ptr(shift), L.ACT_NONE, y.ptr, y.ld, None, 0, x.dtype_code, x.B, x.H, x.W, C, _stream())
+    if ctx.need_grad:
+        world, bn_sync = ctx.bn_world, ctx.bn_sync
+
+        def bwd(sink: GradSink):
+            G = y.g
+            if G is None:
+                return
+            p2 = torch.empty(L.MAX_PARTS * 2 * C, dtype=torch.float32, device=dev)
+            n2 = ctypes.c_int(0)
+            _call("ustrun_bn_bwd_reduce", G.ptr, G.ld, x.ptr, x.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), L.ACT_NONE,
+                  x.dtype_code, x.npix, C, _ptr(p2), ctypes.byref(n2), _stream())
+            parts, n_parts, cnt = p2, n2.value, float(x.npix)
+            if bn_sync is not None:
+                sums2 = torch.empty(2 * C, dtype=torch.float32, device=dev)
+                _call("ustrun_bn_reduce_partials", _ptr(p2), n_parts, C, _ptr(sums2), _stream())
+                bn_sync(sums2)
+                parts, n_parts, cnt = sums2, 1, cnt * world
+            coef = torch.empty(3 * C, dtype=torch.float32, device=dev)
+            dg, a1 = sink.get(bn.weight) if bn.weight is not None else (None, 0)
+            db, a2 = sink.get(bn.bias) if bn.bias is not None else (None, 0)
+            _call("ustrun_bn_bwd_finalize", _ptr(parts), n_parts, C, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db), 1 if (a1 or a2) else 0,
+                  _ptr(coef), _stream())
+            if x.needs_grad:
+                gx = x.like()
+                _call("ustrun_bn_bwd_apply", G.ptr, G.ld, x.ptr, x.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
+                      L.ACT_NONE, gx.ptr, gx.ld, x.dtype_code, x.npix, C, _stream())
+                _assign_grad(x, gx)
+
+        ctx.tape.append(bwd)
+        y.needs_grad = True
+    return y

@@ -1,0 +1,181 @@
+"""The fused SSL training step (Tier B of SURVEY 8b): train.py:638-856 / train_mnms.py:586-771 as
+one call that launches only libustrun_sm100.so kernels and never synchronises with the host.
+
+    trainer = SSLTrainer(model, ema_model, n_classes=2, branch="softmax", base_lr=0.03, max_iterations=60000)
+    out = trainer.step(batch)        # batch: dict of CUDA tensors, see ``SSLTrainer.step``
+
+Order of work (identical to the reference, including the order in which the student's BatchNorm
+running statistics are updated: ulb_w, lb_x, s_ul, s_lu, ulb_s, [lq_s]):
+  1. teacher (train-mode BN, no grad) on ulb_w, CutMix(ulb_w, mix) and CutMix(mix, ulb_w)
+  2. student forward on ulb_w (no grad; only feeds the hardness statistic)           train.py:668
+  3. ONE fused pseudo-label kernel -> 9 uint8 planes                                train.py:649-697
+  4. for each of the four loss branches: forward -> fused CE+Dice pass 1 -> pass 2 (dLoss/dlogits
+     scaled by 1, cw, cw, cw^2) -> backward, accumulating weight gradients in one flat fp32
+     buffer.  The loss is a sum of terms that each depend on one forward and on constant pseudo
+     labels, so branch-at-a-time is mathematically the reference's single backward
+     while holding one branch of activations instead of five.
+  5. [data parallel: bucketed NCCL all-reduce of the flat gradient buffer]
+  6. ONE fused SGD(momentum, wd) + EMA kernel over all tensors                      train.py:848-851
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import bridge
+from . import engine as E
+from .engine import _call, _ptr, _stream
+from .loss_ops import as_u8, term_backward, term_forward
+from .optim import FusedSGDEMA
+
+
+def sigmoid_rampup(current, rampup_length):
+    """utils/ramps.py:19-26 (numpy double arithmetic, bit-identical to the reference)."""
+    if rampup_length == 0:
+        return 1.0
+    phase = 1.0 - float(np.clip(current, 0.0, rampup_length)) / rampup_length
+    return float(np.exp(-5.0 * phase * phase))
+
+
+def pseudo_labels(t1, t2, t3, box, cut_label, cut_mask, choice, threshold, branch, student_logits=None) -> Dict[str, torch.Tensor]:
+    """Fused pseudo-label / ensemble / CutMix-label composition (train.py:649-697).
+
+    t1,t2,t3: teacher logits fp32 NCHW for ulb_w, CutMix(ulb_w, mix), CutMix(mix, ulb_w);
+    box [Bu,H,W] in {0,1}; cut_label/cut_mask: labelled batch (+ bank) labels/masks; choice [Bu].
+    Returns uint8 planes ([Bu,H,W] softmax branch, [Bu,C,H,W] sigmoid branch)."""
+    L.require_device()
+    Bu, C, H, W = t1.shape
+    dev = t1.device
+    t1, t2, t3 = (t.float().contiguous() for t in (t1, t2, t3))
+    s0 = None if student_logits is None else student_logits.float().contiguous()
+    box_u8 = as_u8(box).reshape(Bu, H, W).contiguous()
+    choice_i = choice.to(device=dev, dtype=torch.int32).contiguous()
+    shape = (Bu, H, W) if branch == "softmax" else (Bu, C, H, W)
+    cl = as_u8(cut_label).reshape((-1,) + shape[1:]).contiguous()
+    cm = as_u8(cut_mask).reshape((-1,) + shape[1:]).contiguous()
+    names = ["pseudo_label", "mask", "pseudo_label_w", "mask_w", "pseudo_label_ul", "mask_ul", "pseudo_label_lu", "mask_lu", "stu_pseudo_label"]
+    planes = torch.empty((9,) + shape, dtype=torch.uint8, device=dev)
+    outs = [planes[i] for i in range(9)]
+    ptrs = [_ptr(o) for o in outs]
+    if s0 is None:
+        ptrs[8] = None
+    if branch == "softmax":
+        _call("ustrun_pseudo_label_softmax", _ptr(t1), _ptr(t2), _ptr(t3), _ptr(s0), _ptr(box_u8), _ptr(cl), _ptr(cm), _ptr(choice_i),
+              float(threshold), Bu, C, H, W, *ptrs, _stream())
+    else:
+        _call("ustrun_pseudo_label_sigmoid", _ptr(t1), _ptr(t2), _ptr(t3), _ptr(s0), _ptr(box_u8), _ptr(cl), _ptr(cm), _ptr(choice_i),
+              float(threshold), float(1 - threshold), Bu, C, H, W, *ptrs, _stream())
+    res = dict(zip(names, outs))
+    if s0 is None:
+        del res["stu_pseudo_label"]
+    return res
+
+
+def mix_input(a, b, box_u8, b_index=None) -> E.Act:
+    """NHWC activation of ``a*(1-box) + b[b_index]*box`` (fp32 NCHW sources); box=None converts a."""
+    a = a.float().contiguous()
+    B, C, H, W = a.shape
+    out = E.Act.new(B, H, W, C, device=a.device)
+    _call("ustrun_mix_to_nhwc", _ptr(a), _ptr(b.float().contiguous()) if b is not None else None,
+          _ptr(b_index) if b_index is not None else None, _ptr(box_u8) if box_u8 is not None else None, out.ptr, out.ld, out.dtype_code,
+          B, C, H, W, _stream())
+    return out
+
+
+class SSLTrainer:
+    def __init__(self, model, ema_model, n_classes, branch="softmax", base_lr=0.03, max_iterations=30000, threshold=0.95,
+                 consistency=1.0, consistency_rampup=200.0, ema_decay=0.99, momentum=0.9, weight_decay=1e-4, dp=None,
+                 forward_kwargs=None):
+        self.model, self.ema_model = model, ema_model
+        self.n_classes, self.branch = n_classes, branch
+        self.base_lr, self.lr, self.max_iterations = base_lr, base_lr, max_iterations
+        self.threshold, self.consistency, self.consistency_rampup, self.ema_decay = threshold, consistency, consistency_rampup, ema_decay
+        self.iter_num = 0
+        self.dp = dp
+        self.forward_kwargs = forward_kwargs or {}
+        self.params = list(model.parameters())
+        self.opt = FusedSGDEMA(self.params, list(ema_model.parameters()), momentum=momentum, weight_decay=weight_decay)
+        self._touched = set()
+
+    # -- helpers ---------------------------------------------------------------------------
+    def consistency_weight(self, iter_num):
+        return self.consistency * sigmoid_rampup(iter_num // (self.max_iterations / self.consistency_rampup), self.consistency_rampup)
+
+    def _forward(self, model, a: E.Act, need_grad: bool):
+        ctx = E.Ctx(model.training, need_grad, bn_sync=bridge.BN_SYNC)
+        ctx.bn_world = bridge.BN_WORLD
+        (logits, head_bwd), = model.program(ctx, a, **self.forward_kwargs)
+        return ctx, logits, head_bwd
+
+    def _grad_provider(self, param):
+        self._touched.add(id(param))
+        return self.opt.grad_for(param)
+
+    def _branch(self, a, target_u8, mask_u8, weight):
+        """forward -> loss -> backward of one loss branch; returns loss3 device tensor."""
+        ctx, logits, head_bwd = self._forward(self.model, a, True)
+        loss3, coef = term_forward(logits, target_u8, mask_u8, self.branch)
+        dlogits = term_backward(logits, target_u8, mask_u8, self.branch, coef, gscale=weight)
+        sink = E.GradSink(provider=self._grad_provider)
+        head_bwd(dlogits, sink)
+        ctx.backward(sink)
+        if self.dp is not None:
+            self.dp.on_branch_done()
+        return loss3, logits
+
+    # -- the step ----------------------------------------------------------------------------
+    def step(self, batch, lq=None, keep_logits=False):
+        """batch: lb_x [Bl,C,H,W] fp32, lb_mask ([Bl,H,W] int | [Bl,C,H,W] float), ulb_w, ulb_s,
+        move_transx [Bu,C,H,W], box [Bu,H,W] {0,1}, choice [Bu] int, cut_img [Nc,C,H,W],
+        cut_label, cut_mask (labelled batch + confidence bank).  ``lq``: optional [1,C,H,W] image
+        whose student forward only updates BN running statistics (train.py:740).
+        Returns device tensors (losses, compositions); nothing is copied to the host."""
+        b = batch
+        it = self.iter_num
+        branch = self.branch
+        dev = b["ulb_w"].device
+        box_u8 = as_u8(b["box"]).contiguous()
+        inv_box = 1 - box_u8
+        choice_i = b["choice"].to(device=dev, dtype=torch.int32).contiguous()
+        # 1. teacher
+        _, t1, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], None, None), False)
+        _, t2, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], b["cut_img"], box_u8, choice_i), False)
+        _, t3, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], b["cut_img"], inv_box, choice_i), False)
+        # 2. student on ulb_w (no grad)
+        _, s0, _ = self._forward(self.model, mix_input(b["ulb_w"], None, None), False)
+        # 3. pseudo labels
+        comp = pseudo_labels(t1, t2, t3, box_u8, b["cut_label"], b["cut_mask"], choice_i, self.threshold, branch, student_logits=s0)
+        # 4. four loss branches
+        cw = self.consistency_weight(it)
+        self.opt.zero_grad()
+        self._touched = set()
+        if self.dp is not None:
+            self.dp.begin_step(self.opt)
+        lb_t = as_u8(b["lb_mask"]).contiguous()
+        l_sup, lg_lb = self._branch(mix_input(b["lb_x"], None, None), lb_t, None, 1.0)
+        l_ul, lg_ul = self._branch(mix_input(b["ulb_s"], b["move_transx"], box_u8), comp["pseudo_label_ul"], comp["mask_ul"], cw)
+        l_lu, lg_lu = self._branch(mix_input(b["move_transx"], b["ulb_s"], box_u8), comp["pseudo_label_lu"], comp["mask_lu"], cw)
+        l_s, lg_s = self._branch(mix_input(b["ulb_s"], None, None), comp["pseudo_label_w"], comp["mask_w"], cw * cw)
+        if lq is not None:
+            self._forward(self.model, mix_input(lq, None, None), False)
+        # 5. data-parallel gradient reduction (averaging folded into the optimiser's grad_scale)
+        gscale = 1.0
+        if self.dp is not None:
+            gscale = self.dp.finish_step(self.opt)
+        for i, p in enumerate(self.params):
+            self.opt.set_has_grad(i, id(p) in self._touched)
+        # 6. fused SGD + EMA, then the reference's lr schedule (train.py:854-858)
+        alpha = min(1 - 1 / (it + 1), self.ema_decay)
+        self.opt.step(lr=self.lr, alpha=alpha, grad_scale=gscale)
+        self.lr = self.base_lr * (1.0 - it / self.max_iterations) ** 0.9
+        self.iter_num = it + 1
+        loss = l_sup[0] + cw * (l_ul[0] + l_lu[0] + cw * l_s[0])
+        out = dict(comp)
+        out.update(loss=loss, sup_loss=l_sup[0], unsup_loss_ul=l_ul[0], unsup_loss_lu=l_lu[0], unsup_loss_s=l_s[0], consistency_weight=cw)
+        if keep_logits:
+            out["logits"] = dict(t1=t1, t2=t2, t3=t3, s0=s0, lb=lg_lb, ul=lg_ul, lu=lg_lu, s=lg_s)
+        return out
