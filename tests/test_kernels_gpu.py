@@ -9,6 +9,8 @@ import torch.nn.functional as F
 from util import max_abs, rel_err
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False          # torch's fp32 reference convs must not use TF32
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def _E():

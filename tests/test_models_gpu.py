@@ -13,6 +13,8 @@ from conftest import GOLDEN
 from util import clone_state, load_state_into, rel_err
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False          # torch's fp32 reference convs must not use TF32
+torch.backends.cuda.matmul.allow_tf32 = False
 
 TOL = {"fp32": 1e-4, "bf16": 1e-2}
 
@@ -46,8 +48,9 @@ def _check(name, precision, force_simt, make_mod, oracle_init, oracle_fwd, golde
         x, tgt, msk = torch.from_numpy(fx["x"]), torch.from_numpy(fx["target"]), torch.from_numpy(fx["mask"])
         st = oracle_init()
         o_logits, o_loss, o_grads = _loss_and_grads_oracle(oracle_fwd, clone_state(st), x, tgt, msk, n_classes)
-        # the oracle itself reproduces the reference fixture bit-for-bit on CPU
-        assert np.array_equal(o_logits.numpy(), fx["logits"]) and float(o_loss) == float(fx["loss"])
+        # the oracle reproduces the reference fixture (bit-for-bit in the build container, see
+        # tests/test_oracle_golden.py; another host CPU may pick different oneDNN kernels)
+        assert np.allclose(o_logits.numpy(), fx["logits"], rtol=1e-4, atol=1e-5) and abs(float(o_loss) - float(fx["loss"])) < 1e-5
         mod = load_state_into(make_mod(), st).cuda().train()
         logits, loss, grads = _run_module(mod, x, tgt, msk, n_classes, **fkw)
         tol = TOL[precision]

@@ -1,0 +1,147 @@
+"""CPU: the oracle restatement reproduces the golden fixtures that oracle/make_golden.py produced
+by running the reference's own modules (bit-exact: same torch CPU ops in the same order)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import ssl_step_ref as S
+from oracle import unet_ref as U
+
+torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+
+
+def _digest(v):
+    v = v.detach().double().flatten()
+    return np.concatenate([[v.sum().item(), v.abs().sum().item()], v[:4].numpy()])
+
+
+def _model_case(fixture, init, fwd, n_classes):
+    fx = np.load(os.path.join(GOLDEN, fixture))
+    st = init()
+    params, _ = U.split_state(st)
+    for p in params.values():
+        p.requires_grad_(True)
+    x, tgt, msk = torch.from_numpy(fx["x"]), torch.from_numpy(fx["target"]), torch.from_numpy(fx["mask"])
+    logits = fwd(st, x)
+    loss = S.masked_term(logits, tgt, msk, n_classes, "softmax")
+    loss.backward()
+    assert np.array_equal(logits.detach().numpy(), fx["logits"])
+    assert float(loss) == float(fx["loss"])
+    for k, p in params.items():
+        key = "grad/" + k
+        if key in fx.files:
+            g = p.grad
+            got = np.concatenate([[g.double().norm().item(), g.double().sum().item()], g.flatten()[:6].double().numpy()])
+            np.testing.assert_allclose(got, fx[key], rtol=1e-12, atol=0)
+        else:
+            assert p.grad is None, k
+    for k, v in st.items():
+        np.testing.assert_allclose(_digest(v), fx["state_after/" + k], rtol=1e-12, atol=0, err_msg=k)
+
+
+@pytest.mark.parametrize("c,k", [(1, 2), (3, 3)])
+def test_unet_a_golden(c, k):
+    _model_case(f"unet_a_c{c}_k{k}_32.npz", lambda: U.init_unet_a(c, k, seed=1337), lambda s, x: U.unet_a_forward(s, x, True), k)
+
+
+@pytest.mark.parametrize("c,k,hw", [(3, 3, 32), (1, 2, 48)])
+def test_unet_b_golden(c, k, hw):
+    _model_case(f"unet_b_c{c}_k{k}_{hw}.npz", lambda: U.init_unet_b(c, k, seed=1337), lambda s, x: U.unet_b_forward(s, x, True), k)
+
+
+def test_dsbn_golden():
+    dl = torch.tensor([2, 2, 0, 1])
+
+    def init():
+        torch.manual_seed(1337)
+        enc = U.init_unet_b(3, 2, norm="bn", decoder=False)
+        dec = U.init_rec_decoder(num_classes=2, norm="dsbn", num_domains=3)
+        return {**{"enc." + k: v for k, v in enc.items()}, **{"dec." + k: v for k, v in dec.items()}}
+
+    def fwd(s, t):
+        e = {k[4:]: v for k, v in s.items() if k.startswith("enc.")}
+        d = {k[4:]: v for k, v in s.items() if k.startswith("dec.")}
+        return U.rec_decoder_forward(d, U.unet_b_encoder(e, t, True)[-1], dl, True)
+
+    _model_case("dsbn_encrec.npz", init, fwd, 2)
+    with pytest.raises(TypeError):      # unet.py:142-145: dsbn without a label
+        U.rec_decoder_forward(U.init_rec_decoder(norm="dsbn", num_domains=2, seed=0), torch.zeros(1, 256, 2, 2), None)
+    with pytest.raises(ValueError):     # dsbn.py:31-34
+        U._dsbn({}, "x", torch.zeros(2, 3), [0], True)
+
+
+def test_losses_golden():
+    fx = np.load(os.path.join(GOLDEN, "losses.npz"))
+    for C in (2, 3, 4):
+        logits = torch.from_numpy(fx[f"softmax_C{C}/logits"]).requires_grad_()
+        tgt, msk = torch.from_numpy(fx[f"softmax_C{C}/target"]), torch.from_numpy(fx[f"softmax_C{C}/mask"])
+        for tag, m in (("m", msk), ("n", None)):
+            loss = S.dice_loss_with_mask(logits, tgt.unsqueeze(1), C, mask=m, softmax=True)
+            (g,) = torch.autograd.grad(loss, logits)
+            assert float(loss) == float(fx[f"softmax_C{C}_{tag}/loss"]) and np.array_equal(g.numpy(), fx[f"softmax_C{C}_{tag}/grad"])
+        z = S.dice_loss_with_mask(logits, tgt.unsqueeze(1), C, mask=torch.zeros_like(msk), softmax=True)
+        assert float(z) == float(fx[f"softmax_C{C}_zero_mask/loss"])
+        assert float(z) < 1.0     # F8: class 0 is never masked, so an all-zero mask is not "no loss"
+    logits = torch.from_numpy(fx["sigmoid/logits"]).requires_grad_()
+    tgt, msk = torch.from_numpy(fx["sigmoid/target"]), torch.from_numpy(fx["sigmoid/mask"])
+    for tag, m in (("m", msk), ("n", None)):
+        loss = S.dice_loss_with_mask(logits, tgt.unsqueeze(1), 2, mask=m, sigmoid=True, multi=True)
+        assert float(loss) == float(fx[f"sigmoid_{tag}/loss"])
+    for cur in (0, 1, 37.0, 199, 200, 500):
+        assert S.sigmoid_rampup(cur, 200.0) == float(fx[f"rampup/{cur}"])
+    with pytest.raises(AssertionError):
+        S.dice_loss_with_mask(logits, tgt, 2, softmax=True, sigmoid=True)
+
+
+def test_scalar_schedules():
+    assert S.ema_alpha(0) == 0.0 and S.ema_alpha(1) == 0.5 and S.ema_alpha(10 ** 6) == 0.99     # train.py:91
+    assert S.consistency_weight(0, 30000) == pytest.approx(np.exp(-5.0))
+    assert S.consistency_weight(29999, 30000) == pytest.approx(float(np.exp(-5.0 * (1 - 199 / 200) ** 2)))
+    assert S.poly_lr(0.03, 0, 30000) == 0.03
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "step_*.npz"))), ids=os.path.basename)
+def test_step_golden(path):
+    fx = np.load(path)
+    name = os.path.basename(path)[:-4].split("_")
+    model, branch = name[1], name[2]
+    c, k, hw, B, it, bank = int(name[3][1:]), int(name[4][1:]), int(name[5]), int(name[6][1:]), int(name[7][2:]), int(name[8][4:])
+    torch.manual_seed(1337)
+    if model == "a":
+        st_s, st_t = U.init_unet_a(c, k), U.init_unet_a(c, k)
+        fwd = lambda s, x: U.unet_a_forward(s, x, True)
+    else:
+        st_s, st_t = U.init_unet_b(c, k), U.init_unet_b(c, k)
+        fwd = lambda s, x: U.unet_b_forward(s, x, True)
+    batch = S.synthetic_batch(c, k, hw, hw, B, B, seed=1337, branch=branch, bank=bank)
+    out = S.ssl_step(fwd, st_s, st_t, {}, batch, n_classes=k, branch=branch, iter_num=it, max_iterations=30000, lr=0.03,
+                     threshold=float(fx["threshold"]))
+    assert float(out["loss"]) == float(fx["loss"])
+    for key in ("pseudo_label", "mask", "pseudo_label_w", "mask_w", "pseudo_label_ul", "mask_ul", "pseudo_label_lu", "mask_lu"):
+        assert np.array_equal(out[key].numpy().astype(np.uint8), fx["comp/" + key].astype(np.uint8)), key
+    for k_, v in st_s.items():
+        np.testing.assert_allclose(_digest(v), fx["student_after/" + k_], rtol=1e-12, atol=0, err_msg=k_)
+    for k_, v in st_t.items():
+        np.testing.assert_allclose(_digest(v), fx["teacher_after/" + k_], rtol=1e-12, atol=0, err_msg=k_)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/networks"), reason="reference checkout not present (GPU box)")
+def test_oracle_live_against_reference():
+    """In the build container the reference itself is importable: run it side by side."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r)\n"
+            "import torch\n"
+            "from networks import unet_model\n"
+            "from oracle import unet_ref as U\n"
+            "torch.manual_seed(7); m = unet_model.UNet(1, 2); m.train()\n"
+            "st = U.init_unet_a(1, 2, seed=7)\n"
+            "x = torch.rand(2, 1, 32, 32)\n"
+            "assert torch.equal(m(x), U.unet_a_forward(st, x, True))\n"
+            "print('live-ok')\n") % os.path.dirname(GOLDEN.rstrip('/')).rsplit('/tests', 1)[0]
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "live-ok" in r.stdout, r.stderr[-2000:]

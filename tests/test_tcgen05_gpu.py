@@ -7,6 +7,8 @@ import torch.nn.functional as F
 from util import max_abs, rel_err
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False          # torch's fp32 reference convs must not use TF32
+torch.backends.cuda.matmul.allow_tf32 = False
 
 SHAPES = [  # B, Cin, Cout, H, W
     (2, 64, 64, 16, 16),

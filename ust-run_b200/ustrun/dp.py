@@ -1,0 +1,132 @@
+"""Data parallelism for the SSL step: one process per GPU, torch.distributed (NCCL over
+NVLink/NVSwitch) for the plumbing.  The reference is single-GPU, so this layer is new:
+
+  * gradients: the fused optimiser keeps every gradient in ONE flat fp32 buffer; ``GradBuckets``
+    cuts it into contiguous buckets and all-reduces each bucket on a side stream as soon as the
+    LAST loss branch's backward has written all of its tensors (reverse layer order), overlapping
+    the remaining backward.  The 1/world averaging is folded into the SGD kernel (``grad_scale``).
+  * BatchNorm / DSBN statistics: per layer, per pass, a [2*C] fp32 vector (sum, sum of squares;
+    backward: sum g', sum g' xhat) is summed across ranks before the finalize kernel, giving
+    global-batch BN (G ranks x B images == one device with G*B images).
+The host-side logic is device-agnostic so that it is covered by world_size-2 ``gloo`` tests on CPU.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import bridge
+
+
+class GradBuckets:
+    """Contiguous buckets over a flat gradient buffer; ``mark(i)`` says tensor i's gradient kernel has
+    been enqueued, a bucket is launched when all of its tensors are marked."""
+
+    def __init__(self, flat: torch.Tensor, offsets: List[int], sizes: List[int], bucket_bytes: int = 32 << 20, group=None):
+        self.flat, self.group = flat, group
+        self.offsets, self.sizes = offsets, sizes
+        self.bucket_of, self.ranges = [], []
+        start, cur = 0, 0
+        n = len(offsets)
+        for i in range(n):
+            end = offsets[i + 1] if i + 1 < n else flat.numel()
+            self.bucket_of.append(len(self.ranges))
+            cur = end - start
+            if cur * 4 >= bucket_bytes or i == n - 1:
+                self.ranges.append((start, end))
+                start = end
+        self.members = [[i for i in range(n) if self.bucket_of[i] == b] for b in range(len(self.ranges))]
+        self.comm_stream = torch.cuda.Stream() if flat.is_cuda else None
+        self.reset()
+
+    def reset(self):
+        self.pending = [set(m) for m in self.members]
+        self.launched = [False] * len(self.ranges)
+        self.works = []
+
+    def mark(self, i: int):
+        b = self.bucket_of[i]
+        self.pending[b].discard(i)
+        if not self.pending[b] and not self.launched[b]:
+            self._launch(b)
+
+    def _launch(self, b: int):
+        s, e = self.ranges[b]
+        self.launched[b] = True
+        view = self.flat[s:e]
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                self.works.append(dist.all_reduce(view, group=self.group, async_op=True))
+        else:
+            self.works.append(dist.all_reduce(view, group=self.group, async_op=True))
+
+    def flush(self):
+        """Launch whatever is still pending and make the current stream wait for all buckets."""
+        for b in range(len(self.ranges)):
+            if not self.launched[b]:
+                self._launch(b)
+        for w in self.works:
+            w.wait()
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.works = []
+
+
+class DataParallel:
+    """Attach to an ``SSLTrainer`` (``dp=`` argument).  ``sync_bn`` installs the cross-rank
+    BatchNorm statistics hook used by every conv+BN op."""
+
+    def __init__(self, group=None, bucket_bytes: int = 32 << 20, sync_bn: bool = True):
+        assert dist.is_initialized(), "init_process_group first (backend nccl on GPUs, gloo in CPU tests)"
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.bucket_bytes = bucket_bytes
+        self.buckets: Optional[GradBuckets] = None
+        self.branch = 0
+        self.sync_bn = sync_bn
+        if sync_bn and self.world > 1:
+            bridge.BN_SYNC = self.sum_across_ranks
+            bridge.BN_WORLD = self.world
+
+    def close(self):
+        bridge.BN_SYNC, bridge.BN_WORLD = None, 1
+
+    def sum_across_ranks(self, t: torch.Tensor):
+        dist.all_reduce(t, group=self.group)
+
+    def broadcast_parameters(self, tensors):
+        for t in tensors:
+            dist.broadcast(t, src=0, group=self.group)
+
+    # -- hooks called by SSLTrainer ----------------------------------------------------------
+    def begin_step(self, opt):
+        if self.buckets is None or self.buckets.flat is not opt.flat_grad:
+            sizes = [p.numel() for p in opt.params]
+            self.buckets = GradBuckets(opt.flat_grad, opt.offsets, sizes, self.bucket_bytes, self.group)
+            self._index = {id(p): i for i, p in enumerate(opt.params)}
+        self.buckets.reset()
+        self.branch = 0
+        self._last_requested = None
+
+    def on_branch_done(self):
+        self.branch += 1
+
+    def on_grad_requested(self, param, last_branch: bool):
+        """Called right before a weight-gradient kernel for ``param`` is enqueued: the previously
+        requested tensor's kernel is then already in the stream, so its bucket may go."""
+        if not last_branch or self.world == 1:
+            return
+        if self._last_requested is not None:
+            self.buckets.mark(self._last_requested)
+        self._last_requested = self._index[id(param)]
+
+    def finish_step(self, opt) -> float:
+        if self.world > 1:
+            self.buckets.flush()
+        return 1.0 / self.world

@@ -22,7 +22,11 @@ from . import _lib as L
 
 _PRECISION = os.environ.get("USTRUN_PRECISION", "bf16")
 _FORCE_SIMT = os.environ.get("USTRUN_FORCE_SIMT", "0") == "1"
-LAUNCHES = 0          # kernels-launching C calls issued (bench.py reports it)
+LAUNCHES = 0          # C-ABI calls issued
+KERNELS = 0           # kernels those calls launched (bench.py reports it as gpu_launches)
+PROFILE_EVENTS = None  # bench.py sets this to a list: (kernel class, algorithmic FLOPs, start event, end event)
+_KERNELS_PER_CALL = {"ustrun_conv_wgrad": 2, "ustrun_convT2x2_wgrad": 2, "ustrun_convT2x2_fwd": 4, "ustrun_channel_sum": 2,
+                     "ustrun_ce_dice_softmax_fwd": 2, "ustrun_bce_dice_sigmoid_fwd": 2}
 
 
 def set_precision(mode: str) -> None:
@@ -50,9 +54,21 @@ def _stream():
 
 
 def _call(name, *args):
-    global LAUNCHES
+    global LAUNCHES, KERNELS
     LAUNCHES += 1
+    KERNELS += _KERNELS_PER_CALL.get(name, 1)
     L.call(name, *args)
+
+
+def _profiled(cls, flops, name, *args):
+    """_call bracketed by CUDA events on the launching stream when bench.py profiles."""
+    if PROFILE_EVENTS is None:
+        return _call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _call(name, *args)
+    e1.record()
+    PROFILE_EVENTS.append((cls, flops, e0, e1))
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -220,7 +236,7 @@ def _raw_conv(x: Act, wpk, bias, y: Act, ks, partials=None, out_nchw=None):
     nparts = ctypes.c_int(0)
     impl = L.SIMT if out_nchw is not None else _impl_for(x.C, y.C if y is not None else 0, x.dtype_code)
     cout = out_nchw.shape[1] if out_nchw is not None else y.C
-    _call("ustrun_conv_fwd", impl, x.ptr, x.ld, _ptr(wpk), _ptr(bias), _ptr(out_nchw) if out_nchw is not None else y.ptr,
+    _profiled("tc_conv" if impl == L.TCGEN05 else "simt_conv", 2.0 * x.npix * x.C * cout * ks * ks, "ustrun_conv_fwd", impl, x.ptr, x.ld, _ptr(wpk), _ptr(bias), _ptr(out_nchw) if out_nchw is not None else y.ptr,
           0 if out_nchw is not None else y.ld, x.dtype_code, x.B, x.H, x.W, x.C, cout, ks, 1 if out_nchw is not None else 0,
           _ptr(partials), ctypes.byref(nparts), _stream())
     return nparts.value
@@ -230,7 +246,8 @@ def _wgrad(dy: Act, x: Act, dw: torch.Tensor, accumulate: int, ks: int):
     impl = _impl_for(x.C, dy.C, x.dtype_code)
     nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(impl, x.B, x.H, x.W, x.C, dy.C, ks)
     ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.t.device)
-    _call("ustrun_conv_wgrad", impl, dy.ptr, dy.ld, x.ptr, x.ld, _ptr(dw), accumulate, x.dtype_code, x.B, x.H, x.W, x.C, dy.C, ks,
+    _profiled("tc_wgrad" if impl == L.TCGEN05 else "simt_wgrad", 2.0 * x.npix * x.C * dy.C * ks * ks,
+              "ustrun_conv_wgrad", impl, dy.ptr, dy.ld, x.ptr, x.ld, _ptr(dw), accumulate, x.dtype_code, x.B, x.H, x.W, x.C, dy.C, ks,
           _ptr(ws), int(nbytes), _stream())
 
 

@@ -100,6 +100,7 @@ class SSLTrainer:
         self.params = list(model.parameters())
         self.opt = FusedSGDEMA(self.params, list(ema_model.parameters()), momentum=momentum, weight_decay=weight_decay)
         self._touched = set()
+        self._last_branch = False
 
     # -- helpers ---------------------------------------------------------------------------
     def consistency_weight(self, iter_num):
@@ -113,6 +114,8 @@ class SSLTrainer:
 
     def _grad_provider(self, param):
         self._touched.add(id(param))
+        if self.dp is not None:
+            self.dp.on_grad_requested(param, self._last_branch)
         return self.opt.grad_for(param)
 
     def _branch(self, a, target_u8, mask_u8, weight):
@@ -159,7 +162,9 @@ class SSLTrainer:
         l_sup, lg_lb = self._branch(mix_input(b["lb_x"], None, None), lb_t, None, 1.0)
         l_ul, lg_ul = self._branch(mix_input(b["ulb_s"], b["move_transx"], box_u8), comp["pseudo_label_ul"], comp["mask_ul"], cw)
         l_lu, lg_lu = self._branch(mix_input(b["move_transx"], b["ulb_s"], box_u8), comp["pseudo_label_lu"], comp["mask_lu"], cw)
+        self._last_branch = True          # from here on finished gradient buckets may be all-reduced
         l_s, lg_s = self._branch(mix_input(b["ulb_s"], None, None), comp["pseudo_label_w"], comp["mask_w"], cw * cw)
+        self._last_branch = False
         if lq is not None:
             self._forward(self.model, mix_input(lq, None, None), False)
         # 5. data-parallel gradient reduction (averaging folded into the optimiser's grad_scale)
