@@ -48,6 +48,10 @@ def case(name, make, init, fwd, c, k, hw, B):
     print(f"== {name} c{c} k{k} {hw}x{hw} B{B}: oracle fp32 vs fp64: logits {rel(l32,l64):.2e} loss {abs(float(s32)-float(s64))/abs(float(s64)):.2e}")
     for tag, prec, simt in (("ours fp32", "fp32", True), ("ours bf16 simt", "bf16", True), ("ours bf16 tc", "bf16", False)):
         lo, so, go = ours(make, st, x, tgt, msk, k, prec, simt)
+        if DETAIL and prec == "fp32":
+            for kk in g64:
+                if g64[kk] is not None and float(g64[kk].norm()) > 1e-12:
+                    print(f"      [detail] {kk:50s} ours {rel(go[kk], g64[kk]):.2e} | oracle32 {rel(g32[kk], g64[kk]):.2e}")
         errs = sorted(((rel(go[kk], g64[kk]), rel(g32[kk], g64[kk]), kk) for kk in g64 if g64[kk] is not None and float(g64[kk].norm()) > 1e-12), reverse=True)
         print(f"  {tag}: logits vs fp64 {rel(lo,l64):.2e}  loss {abs(float(so)-float(s64))/abs(float(s64)):.2e}  worst grads (ours|oracle32 vs fp64):")
         for e, e32, kk in errs[:4]:
@@ -58,10 +62,15 @@ def case(name, make, init, fwd, c, k, hw, B):
     allg = torch.cat([ga[kk].flatten().double().cpu() for kk in g64 if g64[kk] is not None]); allr = torch.cat([g64[kk].flatten() for kk in g64 if g64[kk] is not None])
     print(f"  torch autocast-bf16 (cuDNN) same net: logits vs fp64 {rel(la,l64):.2e} loss {abs(float(sa)-float(s64))/abs(float(s64)):.2e} all-grads {float((allg-allr).norm()/allr.norm()):.2e}")
 
+DETAIL = "--detail" in sys.argv
 if __name__ == "__main__":
     torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
     from networks.unet_model import UNet as UA
     from networks.unet import UNet as UB
+    if DETAIL:
+        case("unet_b", lambda: UB(3, 3), lambda: U.init_unet_b(3, 3, seed=1337), lambda s, x: U.unet_b_forward(s, x, True), 3, 3, 32, 2)
+        case("unet_b", lambda: UB(3, 3), lambda: U.init_unet_b(3, 3, seed=1337), lambda s, x: U.unet_b_forward(s, x, True), 3, 3, 64, 2)
+        sys.exit(0)
     for hw, B in ((32, 2), (128, 2), (256, 2)):
         case("unet_a", lambda: UA(1, 2), lambda: U.init_unet_a(1, 2, seed=1337), lambda s, x: U.unet_a_forward(s, x, True), 1, 2, hw, B)
     for hw, B in ((32, 2), (128, 2)):
