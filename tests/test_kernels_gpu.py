@@ -35,7 +35,8 @@ def test_layout_roundtrip(dtype):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("ks,cin,cout,hw", [(3, 3, 16, (16, 16)), (3, 16, 24, (12, 20)), (1, 32, 16, (8, 8)), (3, 64, 64, (16, 16))])
+@pytest.mark.parametrize("ks,cin,cout,hw", [(3, 3, 16, (16, 16)), (3, 16, 24, (12, 20)), (1, 32, 16, (8, 8)), (3, 64, 64, (16, 16)),
+                                          (3, 1, 64, (24, 16)), (1, 64, 2, (16, 16)), (3, 32, 4, (12, 12)), (1, 64, 4, (9, 7))])
 def test_simt_conv_fwd_dgrad_wgrad(dtype, tol, ks, cin, cout, hw):
     from ustrun import _lib as L
     E = _E()

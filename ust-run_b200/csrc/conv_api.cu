@@ -11,6 +11,19 @@ template <typename T>
 int simt_wgrad_launch(const void* a, int lda, const void* b, int ldb, float* dw, int accumulate, ConvGeom g, int Mo, int Nin, void* workspace,
                       long long ws_bytes, cudaStream_t st);
 long long simt_wgrad_ws_bytes(long long P, int Mo, int Nin, int taps);
+bool narrow_in_ok(int Cin, int Cout, int ks);
+bool narrow_out_ok(int Cin, int Cout, int ks);
+bool narrow_wgrad_ok(int Cw, int Cn, int ks);
+long long narrow_wgrad_ws_bytes(long long M, int Cw, int Cn, int ks);
+template <typename T>
+int narrow_in_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ks,
+                     float* partials, int* nparts_host, cudaStream_t st);
+template <typename T>
+int narrow_out_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, float* y_nchw, int B, int H, int W, int Cin,
+                      int Cout, int ks, cudaStream_t st);
+template <typename T>
+int narrow_wgrad_launch(const void* wide, int ldw, int Cw, const void* nar, int ldn, int Cn, int ks, int sgn, int mode, int B, int H, int W,
+                        float* dw, int accumulate, void* workspace, long long ws_bytes, cudaStream_t st);
 
 int tc_conv_fwd(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize,
                 float* partials, int* nparts_host, cudaStream_t st);
@@ -43,8 +56,16 @@ int ustrun_conv_fwd(int impl, const void* x, int ldx, const void* w_packed, cons
     USTRUN_REQUIRE(!out_nchw_f32, "conv_fwd: tcgen05 path writes NHWC bf16 only");
     return tc_conv_fwd(x, ldx, w_packed, bias, y, ldy, B, H, W, Cin, Cout, ksize, partials, nparts_host, st);
   }
-  ConvGeom g{B, H, W, Cin, Cout, ksize, 0, -1};
   float* ynchw = out_nchw_f32 ? (float*)y : nullptr;
+  if (!out_nchw_f32 && narrow_in_ok(Cin, Cout, ksize) && ldy % 8 == 0) {      // first conv / head dgrad: HBM-bound streaming kernel
+    if (dtype == USTRUN_F32) return narrow_in_launch<float>(x, ldx, w_packed, bias, y, ldy, B, H, W, Cin, Cout, ksize, partials, nparts_host, st);
+    return narrow_in_launch<__nv_bfloat16>(x, ldx, w_packed, bias, y, ldy, B, H, W, Cin, Cout, ksize, partials, nparts_host, st);
+  }
+  if (!partials && narrow_out_ok(Cin, Cout, ksize) && ldx % 8 == 0) {          // logits head
+    if (dtype == USTRUN_F32) return narrow_out_launch<float>(x, ldx, w_packed, bias, y, ldy, ynchw, B, H, W, Cin, Cout, ksize, st);
+    return narrow_out_launch<__nv_bfloat16>(x, ldx, w_packed, bias, y, ldy, ynchw, B, H, W, Cin, Cout, ksize, st);
+  }
+  ConvGeom g{B, H, W, Cin, Cout, ksize, 0, -1};
   if (dtype == USTRUN_F32) return simt_conv_launch<float>(x, ldx, w_packed, bias, y, ldy, ynchw, g, partials, nparts_host, st);
   return simt_conv_launch<__nv_bfloat16>(x, ldx, w_packed, bias, y, ldy, ynchw, g, partials, nparts_host, st);
 }
@@ -53,7 +74,10 @@ long long ustrun_conv_wgrad_workspace_bytes(int impl, int B, int H, int W, int C
   // ksize 2 = ConvTranspose2d(k2,s2): Mo = Cin, N = 4*Cout
   if (ksize == 2) return impl == USTRUN_IMPL_TCGEN05 ? tc_convT_wgrad_ws(B, H, W, Cin, Cout) : simt_wgrad_ws_bytes((long long)B * H * W, Cin, Cout, 4);
   if (impl == USTRUN_IMPL_TCGEN05) return tc_conv_wgrad_ws(B, H, W, Cin, Cout, ksize);
-  return simt_wgrad_ws_bytes((long long)B * H * W, Cout, Cin, ksize * ksize);
+  long long generic = simt_wgrad_ws_bytes((long long)B * H * W, Cout, Cin, ksize * ksize), narrow = 0;
+  if (Cin <= 8 && narrow_wgrad_ok(Cout, Cin, ksize)) narrow = narrow_wgrad_ws_bytes((long long)B * H * W, Cout, Cin, ksize);
+  else if (Cout <= 8 && narrow_wgrad_ok(Cin, Cout, ksize)) narrow = narrow_wgrad_ws_bytes((long long)B * H * W, Cin, Cout, ksize);
+  return generic > narrow ? generic : narrow;
 }
 
 int ustrun_conv_wgrad(int impl, const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int dtype, int B, int H, int W,
@@ -62,6 +86,14 @@ int ustrun_conv_wgrad(int impl, const void* dy, int lddy, const void* x, int ldx
   USTRUN_REQUIRE(dy && x && dw && (ksize == 1 || ksize == 3), "conv_wgrad: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == USTRUN_IMPL_TCGEN05) return tc_conv_wgrad(dy, lddy, x, ldx, dw, accumulate, B, H, W, Cin, Cout, ksize, workspace, workspace_bytes, st);
+  if (Cin <= 8 && narrow_wgrad_ok(Cout, Cin, ksize) && lddy % 8 == 0) {        // first conv: wide = dy, narrow = x shifted by +tap
+    if (dtype == USTRUN_F32) return narrow_wgrad_launch<float>(dy, lddy, Cout, x, ldx, Cin, ksize, +1, 0, B, H, W, dw, accumulate, workspace, workspace_bytes, st);
+    return narrow_wgrad_launch<__nv_bfloat16>(dy, lddy, Cout, x, ldx, Cin, ksize, +1, 0, B, H, W, dw, accumulate, workspace, workspace_bytes, st);
+  }
+  if (Cout <= 8 && narrow_wgrad_ok(Cin, Cout, ksize) && ldx % 8 == 0) {         // logits head: wide = x, narrow = dy shifted by -tap
+    if (dtype == USTRUN_F32) return narrow_wgrad_launch<float>(x, ldx, Cin, dy, lddy, Cout, ksize, -1, 1, B, H, W, dw, accumulate, workspace, workspace_bytes, st);
+    return narrow_wgrad_launch<__nv_bfloat16>(x, ldx, Cin, dy, lddy, Cout, ksize, -1, 1, B, H, W, dw, accumulate, workspace, workspace_bytes, st);
+  }
   ConvGeom g{B, H, W, Cin, Cout, ksize, 0, -1};
   if (dtype == USTRUN_F32) return simt_wgrad_launch<float>(dy, lddy, x, ldx, dw, accumulate, g, Cout, Cin, workspace, workspace_bytes, st);
   return simt_wgrad_launch<__nv_bfloat16>(dy, lddy, x, ldx, dw, accumulate, g, Cout, Cin, workspace, workspace_bytes, st);

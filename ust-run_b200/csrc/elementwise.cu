@@ -119,17 +119,24 @@ __global__ void k_bn_finalize(const float* __restrict__ partials, int nparts, in
                               const float* __restrict__ conv_bias, float* running_mean, float* running_var,
                               long long* nbt, float momentum, float eps, int training, float* scale, float* shift,
                               float* mean_out, float* rstd_out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && nbt) *nbt += 1;
+  // one warp per channel: lanes stride over the partial rows, double accumulation, shuffle reduce
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt) *nbt += 1;
   if (c >= C) return;
   float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   float cb = conv_bias ? conv_bias[c] : 0.f;
   if (training) {
     double s = 0.0, q = 0.0;
-    for (int r = 0; r < nparts; ++r) {
+    for (int r = lane; r < nparts; r += 32) {
       s += (double)partials[(size_t)r * 2 * C + c];
       q += (double)partials[(size_t)r * 2 * C + C + c];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane != 0) return;
     double m = s / count;
     double var = q / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -145,8 +152,8 @@ __global__ void k_bn_finalize(const float* __restrict__ partials, int nparts, in
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
   } else {
-    float rstd = rsqrtf(running_var[c] + eps);
-    rstd = 1.0f / sqrtf(running_var[c] + eps);
+    if (lane != 0) return;
+    float rstd = 1.0f / sqrtf(running_var[c] + eps);
     scale[c] = g * rstd;
     shift[c] = b + (cb - running_mean[c]) * g * rstd;
     mean_out[c] = running_mean[c] - cb;
@@ -254,13 +261,19 @@ __global__ void k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __res
 __global__ void k_bn_bwd_finalize(const float* __restrict__ partials, int nparts, int C, double count,
                                   const float* __restrict__ gamma, const float* __restrict__ rstd, float* dgamma,
                                   float* dbeta, int accumulate, float* coef) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int r = 0; r < nparts; ++r) {
+  for (int r = lane; r < nparts; r += 32) {
     s1 += (double)partials[(size_t)r * 2 * C + c];
     s2 += (double)partials[(size_t)r * 2 * C + C + c];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane != 0) return;
   if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
   float g = gamma ? gamma[c] : 1.f;
@@ -507,7 +520,7 @@ int ustrun_bn_finalize(const float* partials, int nparts, int C, double count, c
   USTRUN_REQUIRE(C > 0 && scale && shift && mean && rstd, "bn_finalize: bad args");
   USTRUN_REQUIRE(!training || (partials && nparts > 0 && count > 0), "bn_finalize: training needs partials");
   USTRUN_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval needs running stats");
-  k_bn_finalize<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, beta, conv_bias, running_mean,
+  k_bn_finalize<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, beta, conv_bias, running_mean,
                                                                    running_var, nbt, momentum, eps, training, scale, shift, mean, rstd);
   return check_launch("bn_finalize");
 }
@@ -542,7 +555,7 @@ int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const f
 int ustrun_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* rstd, float* dgamma,
                            float* dbeta, int accumulate, float* coef, void* stream) {
   USTRUN_REQUIRE(partials && nparts > 0 && C > 0 && rstd && coef && count > 0, "bn_bwd_finalize: bad args");
-  k_bn_bwd_finalize<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, rstd, dgamma, dbeta, accumulate, coef);
+  k_bn_bwd_finalize<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, rstd, dgamma, dbeta, accumulate, coef);
   return check_launch("bn_bwd_finalize");
 }
 int ustrun_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, const float* mean, const float* rstd, const float* scale,

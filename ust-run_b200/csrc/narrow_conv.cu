@@ -1,0 +1,246 @@
+// HBM-bound convolutions with one very narrow side (SURVEY App. B marks them "HBM"):
+//   * narrow-K  : first conv of the network (Cin = 1..4 image channels, K = 9*Cin) and the dgrad
+//                 of the logits head (K = taps * n_classes)           -> k_conv_narrow_in
+//   * narrow-N  : the logits head itself (Cout = n_classes <= 8)       -> k_conv_narrow_out
+//   * their weight gradients (one operand 8..256 channels wide, the other <= 8) -> k_wgrad_narrow
+// A tensor-core tile would be >90 % padding here; these kernels stream the wide tensor once with
+// 128-bit accesses and keep the small operand / weights in shared memory or registers.
+#include "common.cuh"
+
+namespace ustrun {
+
+constexpr int NARROW_MAX_W = 6144;   // floats of weights kept in shared memory
+
+// y[p][co] = sum_{tap,ci} x[p+tap][ci] * w[co][tap][ci];  K = taps*Cin small, Cout % 8 == 0
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_conv_narrow_in(const T* __restrict__ x, int ldx, const T* __restrict__ wp, const float* __restrict__ bias, T* __restrict__ y, int ldy,
+                 int B, int H, int W, int Cin, int Cout, int ks, float* __restrict__ partials) {
+  __shared__ __align__(16) float w_s[NARROW_MAX_W];     // [k][co]
+  __shared__ float red[256][16];
+  const int taps = ks * ks, K = taps * Cin;
+  for (int i = threadIdx.x; i < K * Cout; i += 256) {
+    int k = i / Cout, co = i - k * Cout;
+    w_s[i] = to_f(wp[(size_t)co * K + k]);
+  }
+  __syncthreads();
+  const int CG = Cout >> 3, lanes = 256 / CG;
+  const int cg = threadIdx.x % CG, lane = threadIdx.x / CG;
+  const long long M = (long long)B * H * W;
+  const int r = ks >> 1;
+  float bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bs[j] = bias ? bias[cg * 8 + j] : 0.f;
+  float csum[8], csq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { csum[j] = 0.f; csq[j] = 0.f; }
+  for (long long p = (long long)blockIdx.x * lanes + lane; p < M; p += (long long)gridDim.x * lanes) {
+    const int w_ = (int)(p % W), h_ = (int)((p / W) % H), b_ = (int)(p / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int t = 0; t < taps; ++t) {
+      const int hh = h_ + (ks == 3 ? t / 3 : 0) - r, ww = w_ + (ks == 3 ? t % 3 : 0) - r;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      const T* xp = x + (((long long)b_ * H + hh) * W + ww) * ldx;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float xv = to_f(xp[ci]);
+        const float4* wv = reinterpret_cast<const float4*>(w_s + (t * Cin + ci) * Cout + cg * 8);
+        const float4 a = wv[0], c = wv[1];
+        acc[0] = fmaf(xv, a.x, acc[0]); acc[1] = fmaf(xv, a.y, acc[1]); acc[2] = fmaf(xv, a.z, acc[2]); acc[3] = fmaf(xv, a.w, acc[3]);
+        acc[4] = fmaf(xv, c.x, acc[4]); acc[5] = fmaf(xv, c.y, acc[5]); acc[6] = fmaf(xv, c.z, acc[6]); acc[7] = fmaf(xv, c.w, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { csum[j] += acc[j]; csq[j] += acc[j] * acc[j]; acc[j] += bs[j]; }
+    Vec8<T>::store(y + p * ldy + cg * 8, acc);
+  }
+  if (partials) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = csum[j]; red[threadIdx.x][8 + j] = csq[j]; }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * Cout; o += 256) {
+      const int which = o / Cout, c = o - which * Cout;
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[l * CG + (c >> 3)][which * 8 + (c & 7)];
+      partials[(size_t)blockIdx.x * 2 * Cout + o] = s;
+    }
+  }
+}
+
+// Cout <= 8 outputs per pixel, Cin % 8 == 0: 8 threads per pixel each own one 16-byte channel chunk
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_conv_narrow_out(const T* __restrict__ x, int ldx, const T* __restrict__ wp, const float* __restrict__ bias, T* __restrict__ y, int ldy,
+                  float* __restrict__ y_nchw, int B, int H, int W, int Cin, int Cout, int ks) {
+  __shared__ float w_s[NARROW_MAX_W];                   // [tap][ci][co]
+  const int taps = ks * ks, K = taps * Cin;
+  for (int i = threadIdx.x; i < K * Cout; i += 256) {
+    int k = i / Cout, co = i - k * Cout;
+    w_s[i] = to_f(wp[(size_t)co * K + k]);
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const long long M = (long long)B * H * W;
+  const int r = ks >> 1, chunks = Cin >> 3;
+  for (long long p0 = (long long)blockIdx.x * 32; p0 < M; p0 += (long long)gridDim.x * 32) {
+    const long long p = p0 + slot;
+    const bool ok = p < M;
+    const int w_ = (int)(p % W), h_ = (int)((p / W) % H), b_ = (int)(p / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (ok) {
+      for (int t = 0; t < taps; ++t) {
+        const int hh = h_ + (ks == 3 ? t / 3 : 0) - r, ww = w_ + (ks == 3 ? t % 3 : 0) - r;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        const T* xp = x + (((long long)b_ * H + hh) * W + ww) * ldx;
+        for (int c8 = sub; c8 < chunks; c8 += 8) {
+          float xv[8];
+          Vec8<T>::load(xp + c8 * 8, xv);
+          const float* wv = w_s + (t * Cin + c8 * 8) * Cout;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int co = 0; co < 8; ++co)
+              if (co < Cout) acc[co] = fmaf(xv[j], wv[j * Cout + co], acc[co]);
+        }
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < 8; ++co) {
+      acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
+      acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
+      acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 4);
+    }
+    if (ok && sub < Cout) {
+      float v = 0.f;
+#pragma unroll
+      for (int co = 0; co < 8; ++co) v = (co == sub) ? acc[co] : v;
+      if (bias) v += bias[sub];
+      if (y_nchw) y_nchw[(((long long)b_ * Cout + sub) * H + h_) * W + w_] = v;
+      else y[p * ldy + sub] = from_f<T>(v);
+    }
+  }
+}
+
+// acc[wc][tap][nc] = sum_q wide[q][wc] * narrow[q + sgn*tap][nc];  rows of partial sums per (block, lane)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_wgrad_narrow(const T* __restrict__ wide, int ldw, int Cw, const T* __restrict__ nar, int ldn, int Cn, int ks, int sgn, int B, int H, int W,
+               float* __restrict__ ws) {
+  const int taps = ks * ks, WG = Cw >> 3;
+  const int per = WG * taps, lanes = 256 / per;
+  const int lane = threadIdx.x / per;
+  if (lane >= lanes) return;
+  const int idx = threadIdx.x - lane * per;
+  const int wg = idx % WG, t = idx / WG;
+  const int dh = sgn * ((ks == 3 ? t / 3 : 0) - (ks >> 1)), dw = sgn * ((ks == 3 ? t % 3 : 0) - (ks >> 1));
+  const long long M = (long long)B * H * W;
+  float acc[8][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[j][n] = 0.f;
+  for (long long q = (long long)blockIdx.x * lanes + lane; q < M; q += (long long)gridDim.x * lanes) {
+    const int w_ = (int)(q % W), h_ = (int)((q / W) % H), b_ = (int)(q / ((long long)W * H));
+    const int hh = h_ + dh, ww = w_ + dw;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    float wv[8];
+    Vec8<T>::load(wide + q * ldw + wg * 8, wv);
+    const T* np = nar + (((long long)b_ * H + hh) * W + ww) * ldn;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (n < Cn) {
+        const float nv = to_f(np[n]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j][n] = fmaf(wv[j], nv, acc[j][n]);
+      }
+    }
+  }
+  float* row = ws + ((size_t)blockIdx.x * lanes + lane) * ((size_t)Cw * taps * Cn);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n < Cn) row[((size_t)(wg * 8 + j) * taps + t) * Cn + n] = acc[j][n];
+}
+
+// mode 0: dw[(wc*Cn + nc)*taps + t]  (wide = output channels);  mode 1: dw[(nc*Cw + wc)*taps + t]
+__global__ void k_wgrad_narrow_reduce(const float* __restrict__ ws, int rows, int Cw, int taps, int Cn, int mode, float* __restrict__ dw,
+                                      int accumulate) {
+  const int n = Cw * taps * Cn;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int nc = i % Cn, t = (i / Cn) % taps, wc = i / (Cn * taps);
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += (double)ws[(size_t)r * n + i];
+    const size_t o = mode == 0 ? ((size_t)wc * Cn + nc) * taps + t : ((size_t)nc * Cw + wc) * taps + t;
+    dw[o] = (accumulate ? dw[o] : 0.f) + (float)s;
+  }
+}
+
+// ---- host-side eligibility + launches ---------------------------------------------------------
+static inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+bool narrow_in_ok(int Cin, int Cout, int ks) {
+  return Cin * ks * ks <= 72 && Cin <= 8 && Cout % 8 == 0 && pow2(Cout / 8) && Cout / 8 <= 256 && Cin * ks * ks * Cout <= NARROW_MAX_W;
+}
+bool narrow_out_ok(int Cin, int Cout, int ks) { return Cout <= 8 && Cin % 8 == 0 && Cin * ks * ks * Cout <= NARROW_MAX_W; }
+static int narrow_wgrad_grid(long long M, int lanes) {
+  long long g = (M + lanes - 1) / lanes;
+  if (g > 296) g = 296;
+  return (int)(g < 1 ? 1 : g);
+}
+bool narrow_wgrad_ok(int Cw, int Cn, int ks) { return Cn <= 8 && Cw % 8 == 0 && (Cw / 8) * ks * ks <= 256; }
+long long narrow_wgrad_ws_bytes(long long M, int Cw, int Cn, int ks) {
+  const int per = (Cw / 8) * ks * ks, lanes = 256 / per;
+  return (long long)narrow_wgrad_grid(M, lanes) * lanes * Cw * ks * ks * Cn * (long long)sizeof(float);
+}
+
+template <typename T>
+int narrow_in_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ks,
+                     float* partials, int* nparts_host, cudaStream_t st) {
+  const int lanes = 256 / (Cout / 8);
+  long long M = (long long)B * H * W;
+  long long g = (M + lanes - 1) / lanes;
+  if (g > 592) g = 592;
+  if (nparts_host) *nparts_host = (int)g;
+  k_conv_narrow_in<T><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, B, H, W, Cin, Cout, ks, partials);
+  return check_launch("conv_narrow_in");
+}
+template <typename T>
+int narrow_out_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, float* y_nchw, int B, int H, int W, int Cin,
+                      int Cout, int ks, cudaStream_t st) {
+  long long M = (long long)B * H * W;
+  long long g = (M + 31) / 32;
+  if (g > 148 * 16) g = 148 * 16;
+  k_conv_narrow_out<T><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, y_nchw, B, H, W, Cin, Cout, ks);
+  return check_launch("conv_narrow_out");
+}
+template <typename T>
+int narrow_wgrad_launch(const void* wide, int ldw, int Cw, const void* nar, int ldn, int Cn, int ks, int sgn, int mode, int B, int H, int W,
+                        float* dw, int accumulate, void* workspace, long long ws_bytes, cudaStream_t st) {
+  long long M = (long long)B * H * W;
+  const int per = (Cw / 8) * ks * ks, lanes = 256 / per;
+  const int grid = narrow_wgrad_grid(M, lanes);
+  long long need = narrow_wgrad_ws_bytes(M, Cw, Cn, ks);
+  if (!workspace || ws_bytes < need) { set_error("narrow wgrad: workspace too small (%lld < %lld)", ws_bytes, need); return USTRUN_ERR_ARG; }
+  k_wgrad_narrow<T><<<grid, 256, 0, st>>>((const T*)wide, ldw, Cw, (const T*)nar, ldn, Cn, ks, sgn, B, H, W, (float*)workspace);
+  int rc = check_launch("wgrad_narrow");
+  if (rc) return rc;
+  const int n = Cw * ks * ks * Cn;
+  k_wgrad_narrow_reduce<<<(n + 127) / 128, 128, 0, st>>>((const float*)workspace, grid * lanes, Cw, ks * ks, Cn, mode, dw, accumulate);
+  return check_launch("wgrad_narrow_reduce");
+}
+
+#define INST(T)                                                                                                                              \
+  template int narrow_in_launch<T>(const void*, int, const void*, const float*, void*, int, int, int, int, int, int, int, float*, int*,     \
+                                   cudaStream_t);                                                                                            \
+  template int narrow_out_launch<T>(const void*, int, const void*, const float*, void*, int, float*, int, int, int, int, int, int,           \
+                                    cudaStream_t);                                                                                           \
+  template int narrow_wgrad_launch<T>(const void*, int, int, const void*, int, int, int, int, int, int, int, int, float*, int, void*,        \
+                                      long long, cudaStream_t);
+INST(float)
+INST(__nv_bfloat16)
+
+}  // namespace ustrun
