@@ -162,17 +162,22 @@ __global__ void k_bn_finalize(const float* __restrict__ partials, int nparts, in
 }
 
 template <typename T>
-__global__ void k_bn_act(const T* __restrict__ x, int ldx, const float* __restrict__ scale, const float* __restrict__ shift,
-                         int act, T* __restrict__ y, int ldy, long long npix, int C) {
-  int CG = C >> 3;
-  long long n = npix * CG;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long p = i / CG;
-    float v[8], sc[8], sh[8];
+__global__ void __launch_bounds__(256)
+k_bn_act(const T* __restrict__ x, int ldx, const float* __restrict__ scale, const float* __restrict__ shift,
+         int act, T* __restrict__ y, int ldy, long long npix, int C) {
+  // (gridDim.x * 256) % (C/8) == 0 (host): one channel group per thread, scale/shift in registers
+  const int CG = C >> 3;
+  const long long n = npix * CG, stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cg = (int)(i % CG);
+  float sc[8], sh[8];
+  Vec8<float>::load(scale + cg * 8, sc);
+  Vec8<float>::load(shift + cg * 8, sh);
+#pragma unroll 4
+  for (; i < n; i += stride) {
+    const long long p = i / CG;
+    float v[8];
     Vec8<T>::load(x + p * ldx + cg * 8, v);
-    Vec8<float>::load(scale + cg * 8, sc);
-    Vec8<float>::load(shift + cg * 8, sh);
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = act_fwd(fmaf(v[k], sc[k], sh[k]), act);
     Vec8<T>::store(y + p * ldy + cg * 8, v);
@@ -283,25 +288,30 @@ __global__ void k_bn_bwd_finalize(const float* __restrict__ partials, int nparts
 }
 
 template <typename T>
-__global__ void k_bn_bwd_apply(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ldx,
-                               const float* __restrict__ mean, const float* __restrict__ rstd,
-                               const float* __restrict__ scale, const float* __restrict__ shift,
-                               const float* __restrict__ coef, int act, T* __restrict__ dx, int lddx, long long npix, int C) {
-  int CG = C >> 3;
-  long long n = npix * CG;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long p = i / CG;
-    float gv[8], xv[8], mu[8], rs[8], sc[8], sh[8], a[8], b[8], d[8], o[8];
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ldx, const float* __restrict__ mean,
+               const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
+               const float* __restrict__ coef, int act, T* __restrict__ dx, int lddx, long long npix, int C) {
+  // host guarantees (gridDim.x * 256) % (C/8) == 0: a thread keeps one channel group, so the 7 per-channel
+  // vectors live in registers and the loop streams only g and x (2 x 16 B in, 16 B out)
+  const int CG = C >> 3;
+  const long long n = npix * CG, stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cg = (int)(i % CG);
+  float mu[8], rs[8], sc[8], sh[8], a[8], b[8], d[8];
+  Vec8<float>::load(mean + cg * 8, mu);
+  Vec8<float>::load(rstd + cg * 8, rs);
+  Vec8<float>::load(scale + cg * 8, sc);
+  Vec8<float>::load(shift + cg * 8, sh);
+  Vec8<float>::load(coef + cg * 8, a);
+  Vec8<float>::load(coef + C + cg * 8, b);
+  Vec8<float>::load(coef + 2 * C + cg * 8, d);
+#pragma unroll 2
+  for (; i < n; i += stride) {
+    const long long p = i / CG;
+    float gv[8], xv[8], o[8];
     Vec8<T>::load(g + p * ldg + cg * 8, gv);
     Vec8<T>::load(x + p * ldx + cg * 8, xv);
-    Vec8<float>::load(mean + cg * 8, mu);
-    Vec8<float>::load(rstd + cg * 8, rs);
-    Vec8<float>::load(scale + cg * 8, sc);
-    Vec8<float>::load(shift + cg * 8, sh);
-    Vec8<float>::load(coef + cg * 8, a);
-    Vec8<float>::load(coef + C + cg * 8, b);
-    Vec8<float>::load(coef + 2 * C + cg * 8, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float gp = gv[k] * act_grad(fmaf(xv[k], sc[k], sh[k]), act);
@@ -535,7 +545,9 @@ int ustrun_bn_act_fwd(const void* x, int ldx, const float* scale, const float* s
                                                                                                ldy, (T*)pooled, ldp, B, H, W, C)));
   } else {
     long long n = npix * (C / 8);
-    DISPATCH_DTYPE(dtype, (k_bn_act<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, scale, shift, act, (T*)y, ldy, npix, C)));
+    int grid = grid_for(n, 256);
+    while (((long long)grid * 256) % (C / 8)) ++grid;          // a thread must keep its channel group
+    DISPATCH_DTYPE(dtype, (k_bn_act<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, scale, shift, act, (T*)y, ldy, npix, C)));
   }
   return check_launch("bn_act_fwd");
 }
@@ -562,8 +574,10 @@ int ustrun_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, const fl
                         const float* shift, const float* coef, int act, void* dx, int lddx, int dtype, long long npix, int C, void* stream) {
   USTRUN_REQUIRE(g && x && dx && coef && C % 8 == 0 && ldg % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: bad args");
   long long n = npix * (C / 8);
-  DISPATCH_DTYPE(dtype, (k_bn_bwd_apply<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale,
-                                                                                              shift, coef, act, (T*)dx, lddx, npix, C)));
+  int grid = grid_for(n, 256);
+  while (((long long)grid * 256) % (C / 8)) ++grid;            // a thread must keep its channel group
+  DISPATCH_DTYPE(dtype, (k_bn_bwd_apply<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale,
+                                                                                  shift, coef, act, (T*)dx, lddx, npix, C)));
   return check_launch("bn_bwd_apply");
 }
 int ustrun_maxpool_bwd(const void* y, int ldy, const void* dpool, int ldp, const void* gskip, int ldgs, void* gout, int ldgo, int dtype,

@@ -124,15 +124,16 @@ k_conv_narrow_out(const T* __restrict__ x, int ldx, const T* __restrict__ wp, co
   }
 }
 
-// acc[wc][tap][nc] = sum_q wide[q][wc] * narrow[q + sgn*tap][nc];  rows of partial sums per (block, lane)
+// acc[wc][tap][nc] = sum_q wide[q][wc] * narrow[q + sgn*tap][nc];  one row of partial sums per block
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_wgrad_narrow(const T* __restrict__ wide, int ldw, int Cw, const T* __restrict__ nar, int ldn, int Cn, int ks, int sgn, int B, int H, int W,
                float* __restrict__ ws) {
+  __shared__ float red[8192];                      // [per][8*Cn] block reduction over the pixel lanes
   const int taps = ks * ks, WG = Cw >> 3;
   const int per = WG * taps, lanes = 256 / per;
   const int lane = threadIdx.x / per;
-  if (lane >= lanes) return;
+  const bool active = lane < lanes;
   const int idx = threadIdx.x - lane * per;
   const int wg = idx % WG, t = idx / WG;
   const int dh = sgn * ((ks == 3 ? t / 3 : 0) - (ks >> 1)), dw = sgn * ((ks == 3 ? t % 3 : 0) - (ks >> 1));
@@ -142,41 +143,64 @@ k_wgrad_narrow(const T* __restrict__ wide, int ldw, int Cw, const T* __restrict_
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int n = 0; n < 8; ++n) acc[j][n] = 0.f;
-  for (long long q = (long long)blockIdx.x * lanes + lane; q < M; q += (long long)gridDim.x * lanes) {
-    const int w_ = (int)(q % W), h_ = (int)((q / W) % H), b_ = (int)(q / ((long long)W * H));
-    const int hh = h_ + dh, ww = w_ + dw;
-    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    float wv[8];
-    Vec8<T>::load(wide + q * ldw + wg * 8, wv);
-    const T* np = nar + (((long long)b_ * H + hh) * W + ww) * ldn;
+  if (active) {
+#pragma unroll 4
+    for (long long q = (long long)blockIdx.x * lanes + lane; q < M; q += (long long)gridDim.x * lanes) {
+      const int w_ = (int)(q % W), h_ = (int)((q / W) % H), b_ = (int)(q / ((long long)W * H));
+      const int hh = h_ + dh, ww = w_ + dw;
+      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+      float wv[8];
+      Vec8<T>::load(wide + q * ldw + wg * 8, wv);
+      const T* np = nar + (((long long)b_ * H + (ok ? hh : h_)) * W + (ok ? ww : w_)) * ldn;
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      if (n < Cn) {
-        const float nv = to_f(np[n]);
+      for (int n = 0; n < 8; ++n) {
+        if (n < Cn) {
+          const float nv = ok ? to_f(np[n]) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j][n] = fmaf(wv[j], nv, acc[j][n]);
+          for (int j = 0; j < 8; ++j) acc[j][n] = fmaf(wv[j], nv, acc[j][n]);
+        }
       }
     }
   }
-  float* row = ws + ((size_t)blockIdx.x * lanes + lane) * ((size_t)Cw * taps * Cn);
+  // sequential rounds: lane l adds into shared memory, lane 0 ends up with the block total
+  const int width = 8 * Cn;
+  for (int l = 0; l < lanes; ++l) {
+    if (active && lane == l) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int n = 0; n < 8; ++n)
-      if (n < Cn) row[((size_t)(wg * 8 + j) * taps + t) * Cn + n] = acc[j][n];
+        for (int n = 0; n < 8; ++n)
+          if (n < Cn) {
+            float* p = &red[idx * width + j * Cn + n];
+            *p = (l == 0 ? 0.f : *p) + acc[j][n];
+          }
+    }
+    __syncthreads();
+  }
+  if (active && lane == 0) {
+    float* row = ws + (size_t)blockIdx.x * ((size_t)Cw * taps * Cn);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+        if (n < Cn) row[((size_t)(wg * 8 + j) * taps + t) * Cn + n] = red[idx * width + j * Cn + n];
+  }
 }
 
-// mode 0: dw[(wc*Cn + nc)*taps + t]  (wide = output channels);  mode 1: dw[(nc*Cw + wc)*taps + t]
+// mode 0: dw[(wc*Cn + nc)*taps + t]  (wide = output channels);  mode 1: dw[(nc*Cw + wc)*taps + t]; one warp per element
 __global__ void k_wgrad_narrow_reduce(const float* __restrict__ ws, int rows, int Cw, int taps, int Cn, int mode, float* __restrict__ dw,
                                       int accumulate) {
   const int n = Cw * taps * Cn;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int nc = i % Cn, t = (i / Cn) % taps, wc = i / (Cn * taps);
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += (double)ws[(size_t)r * n + i];
-    const size_t o = mode == 0 ? ((size_t)wc * Cn + nc) * taps + t : ((size_t)nc * Cw + wc) * taps + t;
-    dw[o] = (accumulate ? dw[o] : 0.f) + (float)s;
-  }
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int r = lane; r < rows; r += 32) s += (double)ws[(size_t)r * n + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
+  const int nc = i % Cn, t = (i / Cn) % taps, wc = i / (Cn * taps);
+  const size_t o = mode == 0 ? ((size_t)wc * Cn + nc) * taps + t : ((size_t)nc * Cw + wc) * taps + t;
+  dw[o] = (accumulate ? dw[o] : 0.f) + (float)s;
 }
 
 // ---- host-side eligibility + launches ---------------------------------------------------------
@@ -187,14 +211,16 @@ bool narrow_in_ok(int Cin, int Cout, int ks) {
 }
 bool narrow_out_ok(int Cin, int Cout, int ks) { return Cout <= 8 && Cin % 8 == 0 && Cin * ks * ks * Cout <= NARROW_MAX_W; }
 static int narrow_wgrad_grid(long long M, int lanes) {
-  long long g = (M + lanes - 1) / lanes;
-  if (g > 296) g = 296;
+  long long g = (M + lanes - 1) / lanes;          // aim for ~8K pixel lanes in flight
+  long long cap = (8192 + lanes - 1) / lanes;
+  if (cap > 148 * 16) cap = 148 * 16;
+  if (g > cap) g = cap;
   return (int)(g < 1 ? 1 : g);
 }
-bool narrow_wgrad_ok(int Cw, int Cn, int ks) { return Cn <= 8 && Cw % 8 == 0 && (Cw / 8) * ks * ks <= 256; }
+bool narrow_wgrad_ok(int Cw, int Cn, int ks) { return Cn <= 8 && Cw % 8 == 0 && (Cw / 8) * ks * ks <= 128; }
 long long narrow_wgrad_ws_bytes(long long M, int Cw, int Cn, int ks) {
   const int per = (Cw / 8) * ks * ks, lanes = 256 / per;
-  return (long long)narrow_wgrad_grid(M, lanes) * lanes * Cw * ks * ks * Cn * (long long)sizeof(float);
+  return (long long)narrow_wgrad_grid(M, lanes) * Cw * ks * ks * Cn * (long long)sizeof(float);
 }
 
 template <typename T>
@@ -229,7 +255,7 @@ int narrow_wgrad_launch(const void* wide, int ldw, int Cw, const void* nar, int 
   int rc = check_launch("wgrad_narrow");
   if (rc) return rc;
   const int n = Cw * ks * ks * Cn;
-  k_wgrad_narrow_reduce<<<(n + 127) / 128, 128, 0, st>>>((const float*)workspace, grid * lanes, Cw, ks * ks, Cn, mode, dw, accumulate);
+  k_wgrad_narrow_reduce<<<(n + 7) / 8, 256, 0, st>>>((const float*)workspace, grid, Cw, ks * ks, Cn, mode, dw, accumulate);
   return check_launch("wgrad_narrow_reduce");
 }
 

@@ -196,17 +196,17 @@ k_wgrad_simt(const T* __restrict__ a, int lda, const T* __restrict__ bsrc, int l
   }
 }
 
-// dw[(m*Nin + c)*taps + t] (+)= sum_s ws[s][m][t*Nin + c]
+// dw[(m*Nin + c)*taps + t] (+)= sum_s ws[s][m][t*Nin + c]   (threads walk ws order: coalesced reads of every split)
 __global__ void k_wgrad_reduce(const float* __restrict__ ws, int splits, int Mo, int Nin, int taps, float* __restrict__ dw, int accumulate) {
   long long n = (long long)Mo * Nin * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int t = (int)(i % taps);
-    int c = (int)((i / taps) % Nin);
-    int m = (int)(i / ((long long)taps * Nin));
-    size_t src = (size_t)m * taps * Nin + (size_t)t * Nin + c;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(j % Nin);
+    int t = (int)((j / Nin) % taps);
+    int m = (int)(j / ((long long)taps * Nin));
     float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[(size_t)k * n + src];
-    dw[i] = (accumulate ? dw[i] : 0.f) + s;
+    for (int k = 0; k < splits; ++k) s += ws[(size_t)k * n + j];
+    size_t o = ((size_t)m * Nin + c) * taps + t;
+    dw[o] = (accumulate ? dw[o] : 0.f) + s;
   }
 }
 
