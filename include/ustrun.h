@@ -135,6 +135,15 @@ int ustrun_mix_to_nhwc(const float* a, const float* b, const int* b_index, const
 int ustrun_ce_dice_softmax_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
                                int W, float ce_w, float dice_w, const float* class_weight, float* workspace,
                                float* coef, float* loss_out, void* stream);
+/* The two halves of the forward, for data parallelism: `partials` writes *nparts_host rows of (3C+1)
+ * partial sums; the caller may sum rows (ustrun_reduce_rows) and all-reduce them across ranks, then
+ * `finalize` with the GLOBAL pixel count gives the global-batch loss and coefficients. */
+int ustrun_ce_dice_softmax_partials(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
+                                    int W, float* workspace, int* nparts_host, void* stream);
+int ustrun_ce_dice_softmax_finalize(const float* workspace, int nparts, int C, double npix_total, float ce_w, float dice_w,
+                                    const float* class_weight, float* coef, float* loss_out, void* stream);
+/* out[c] = sum_r rows[r][c] */
+int ustrun_reduce_rows(const float* rows, int nrows, int ncols, float* out, void* stream);
 /* dlogits (+)= gscale * (*upstream, nullable => 1) * dLoss/dlogits */
 int ustrun_ce_dice_softmax_bwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
                                int W, const float* coef, const float* upstream, float gscale, float* dlogits,
@@ -144,6 +153,10 @@ int ustrun_ce_dice_softmax_bwd(const float* logits, const uint8_t* target, const
 int ustrun_bce_dice_sigmoid_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
                                 int W, float ce_w, float dice_w, float* workspace, float* coef, float* loss_out,
                                 void* stream);
+int ustrun_bce_dice_sigmoid_partials(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
+                                     int W, float* workspace, int* nparts_host, void* stream);
+int ustrun_bce_dice_sigmoid_finalize(const float* workspace, int nparts, double nelem_total, float ce_w, float dice_w,
+                                     float* coef, float* loss_out, void* stream);
 int ustrun_bce_dice_sigmoid_bwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H,
                                 int W, const float* coef, const float* upstream, float gscale, float* dlogits,
                                 int accumulate, void* stream);

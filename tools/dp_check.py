@@ -1,0 +1,65 @@
+"""Data-parallel parity on real GPUs (run under torchrun, world_size W):
+W ranks x (B_l+B_u) images with NCCL gradient all-reduce, cross-rank BN statistics and global
+CE/Dice sums must reproduce ONE process stepping on the concatenated batch.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/dp_check.py
+"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ust-run_b200"))
+import torch, torch.distributed as dist
+from oracle import ssl_step_ref as S
+from ustrun import engine as E
+from ustrun.step import SSLTrainer
+from ustrun.dp import DataParallel
+from networks.unet_model import UNet
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    precision = os.environ.get("USTRUN_PRECISION", "fp32")
+    E.set_precision(precision)
+    c, k, hw, B = 1, 2, 64, 2
+    full = S.synthetic_batch(c, k, hw, hw, B * world, B * world, seed=1337)
+    full["choice"] = full["choice"] % (B * world)
+    def models():
+        torch.manual_seed(1337)
+        s, t = UNet(c, k), UNet(c, k)
+        t.load_state_dict(s.state_dict())
+        for p in t.parameters(): p.detach_()
+        return s.cuda().train(), t.cuda().train()
+    # --- data parallel: rank r owns images [r*B, (r+1)*B) of every batch tensor; the CutMix partner pool (cut_*) is replicated
+    sl = slice(rank * B, (rank + 1) * B)
+    local_batch = {kk: (v[sl] if kk in ("lb_x", "lb_mask", "ulb_w", "ulb_s", "move_transx", "box", "choice") else v) for kk, v in full.items()}
+    dp = DataParallel(sync_bn=True, global_loss=True, bucket_bytes=8 << 20)
+    s_dp, t_dp = models()
+    tr = SSLTrainer(s_dp, t_dp, n_classes=k, threshold=0.6, dp=dp)
+    tr.iter_num = 3000
+    outs = [tr.step({kk: v.cuda() for kk, v in local_batch.items()}) for _ in range(2)]
+    torch.cuda.synchronize()
+    dp.close()
+    # --- single process on the concatenated batch (every rank computes it; rank 0 reports)
+    s_1, t_1 = models()
+    tr1 = SSLTrainer(s_1, t_1, n_classes=k, threshold=0.6)
+    tr1.iter_num = 3000
+    outs1 = [tr1.step({kk: v.cuda() for kk, v in full.items()}) for _ in range(2)]
+    torch.cuda.synchronize()
+    def rel(a, b): return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+    worst = max(rel(p, q) for p, q in zip(s_dp.parameters(), s_1.parameters()))
+    worst_t = max(rel(p, q) for p, q in zip(t_dp.parameters(), t_1.parameters()))
+    worst_rs = max(rel(a, b) for (n1, a), (n2, b) in zip(s_dp.named_buffers(), s_1.named_buffers()) if "running" in n1)
+    dl = [abs(float(o["loss"]) - float(o1["loss"])) / abs(float(o1["loss"])) for o, o1 in zip(outs, outs1)]
+    same = all(torch.equal(outs[0][kk], outs1[0][kk][sl]) for kk in ("pseudo_label", "mask_w"))
+    gathered = [torch.zeros(1, device="cuda") for _ in range(world)]
+    dist.all_gather(gathered, torch.tensor([worst], device="cuda"))
+    if rank == 0:
+        print(f"dp_check world={world} precision={precision}: loss rel diff per step {dl}, student weights {worst:.2e} (all ranks {[float(g) for g in gathered]}), "
+              f"teacher {worst_t:.2e}, running stats {worst_rs:.2e}, step-0 masks identical {same}")
+        tol = 2e-4 if precision == "fp32" else 5e-2
+        assert worst < tol and worst_t < tol and worst_rs < tol and max(dl) < tol, "data-parallel step != single-process step on the concatenated batch"
+        print("dp_check OK")
+    dist.destroy_process_group()
+
+if __name__ == "__main__":
+    main()

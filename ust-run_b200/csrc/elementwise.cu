@@ -238,6 +238,7 @@ __global__ void k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __res
     Vec8<float>::load(rstd + cg * 8, rs);
     Vec8<float>::load(scale + cg * 8, sc);
     Vec8<float>::load(shift + cg * 8, sh);
+#pragma unroll 4
     for (long long p = (long long)blockIdx.x * lanes + tid / CG; p < npix; p += (long long)gridDim.x * lanes) {
       float gv[8], xv[8];
       Vec8<T>::load(g + p * ldg + cg * 8, gv);

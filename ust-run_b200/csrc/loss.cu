@@ -348,6 +348,16 @@ __global__ void __launch_bounds__(256) k_bce_dice_pass2(const float* __restrict_
   }
 }
 
+__global__ void k_reduce_rows(const float* __restrict__ rows, int nrows, int ncols, float* __restrict__ out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= ncols) return;
+  double s = 0.0;
+  for (int r = lane; r < nrows; r += 32) s += (double)rows[(size_t)r * ncols + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[c] = (float)s;
+}
+
 static inline int loss_grid(long long n) {
   long long b = (n + 255) / 256;
   if (b > USTRUN_MAX_PARTS) b = USTRUN_MAX_PARTS;
@@ -418,15 +428,34 @@ int ustrun_mix_to_nhwc(const float* a, const float* b, const int* b_index, const
   return check_launch("mix_to_nhwc");
 }
 
-int ustrun_ce_dice_softmax_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W, float ce_w,
-                               float dice_w, const float* class_weight, float* workspace, float* coef, float* loss_out, void* stream) {
-  USTRUN_REQUIRE(logits && target && workspace && coef && loss_out && B > 0 && H > 0 && W > 0, "ce_dice_softmax_fwd: null/empty arg");
+int ustrun_reduce_rows(const float* rows, int nrows, int ncols, float* out, void* stream) {
+  USTRUN_REQUIRE(rows && out && nrows > 0 && ncols > 0, "reduce_rows: bad args");
+  k_reduce_rows<<<ceil_div(ncols, 8), 256, 0, (cudaStream_t)stream>>>(rows, nrows, ncols, out);
+  return check_launch("reduce_rows");
+}
+
+int ustrun_ce_dice_softmax_partials(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W,
+                                    float* workspace, int* nparts_host, void* stream) {
+  USTRUN_REQUIRE(logits && target && workspace && nparts_host && B > 0 && H > 0 && W > 0, "ce_dice_softmax_partials: null/empty arg");
   const long long n = (long long)B * H * W;
   const int grid = loss_grid(n);
-  cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_C(C, (k_ce_dice_pass1<kC><<<grid, 256, 0, st>>>(logits, target, mask, B, H * W, workspace)));
-  k_ce_dice_finalize<<<1, 32, 0, st>>>(workspace, grid, C, (double)n, ce_w, dice_w, class_weight, coef, loss_out);
-  return check_launch("ce_dice_softmax_fwd");
+  *nparts_host = grid;
+  DISPATCH_C(C, (k_ce_dice_pass1<kC><<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, mask, B, H * W, workspace)));
+  return check_launch("ce_dice_softmax_partials");
+}
+int ustrun_ce_dice_softmax_finalize(const float* workspace, int nparts, int C, double npix_total, float ce_w, float dice_w,
+                                    const float* class_weight, float* coef, float* loss_out, void* stream) {
+  USTRUN_REQUIRE(workspace && nparts > 0 && C >= 2 && C <= 8 && npix_total > 0 && coef && loss_out, "ce_dice_softmax_finalize: bad args");
+  k_ce_dice_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, nparts, C, npix_total, ce_w, dice_w, class_weight, coef, loss_out);
+  return check_launch("ce_dice_softmax_finalize");
+}
+int ustrun_ce_dice_softmax_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W, float ce_w,
+                               float dice_w, const float* class_weight, float* workspace, float* coef, float* loss_out, void* stream) {
+  USTRUN_REQUIRE(coef && loss_out, "ce_dice_softmax_fwd: null arg");
+  int nparts = 0;
+  int rc = ustrun_ce_dice_softmax_partials(logits, target, mask, B, C, H, W, workspace, &nparts, stream);
+  if (rc) return rc;
+  return ustrun_ce_dice_softmax_finalize(workspace, nparts, C, (double)B * H * W, ce_w, dice_w, class_weight, coef, loss_out, stream);
 }
 int ustrun_ce_dice_softmax_bwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W, const float* coef,
                                const float* upstream, float gscale, float* dlogits, int accumulate, void* stream) {
@@ -437,15 +466,28 @@ int ustrun_ce_dice_softmax_bwd(const float* logits, const uint8_t* target, const
   DISPATCH_C(C, (k_ce_dice_pass2<kC><<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, mask, B, H * W, coef, upstream, gscale, dlogits, accumulate)));
   return check_launch("ce_dice_softmax_bwd");
 }
-int ustrun_bce_dice_sigmoid_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W, float ce_w,
-                                float dice_w, float* workspace, float* coef, float* loss_out, void* stream) {
-  USTRUN_REQUIRE(logits && target && workspace && coef && loss_out && B > 0 && C > 0 && H > 0 && W > 0, "bce_dice_sigmoid_fwd: null/empty arg");
+int ustrun_bce_dice_sigmoid_partials(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W,
+                                     float* workspace, int* nparts_host, void* stream) {
+  USTRUN_REQUIRE(logits && target && workspace && nparts_host && B > 0 && C > 0 && H > 0 && W > 0, "bce_dice_sigmoid_partials: null/empty arg");
   const long long n = (long long)B * C * H * W;
   const int grid = loss_grid(n);
-  cudaStream_t st = (cudaStream_t)stream;
-  k_bce_dice_pass1<<<grid, 256, 0, st>>>(logits, target, mask, n, workspace);
-  k_bce_dice_finalize<<<1, 32, 0, st>>>(workspace, grid, (double)n, ce_w, dice_w, coef, loss_out);
-  return check_launch("bce_dice_sigmoid_fwd");
+  *nparts_host = grid;
+  k_bce_dice_pass1<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, mask, n, workspace);
+  return check_launch("bce_dice_sigmoid_partials");
+}
+int ustrun_bce_dice_sigmoid_finalize(const float* workspace, int nparts, double nelem_total, float ce_w, float dice_w, float* coef,
+                                     float* loss_out, void* stream) {
+  USTRUN_REQUIRE(workspace && nparts > 0 && nelem_total > 0 && coef && loss_out, "bce_dice_sigmoid_finalize: bad args");
+  k_bce_dice_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, nparts, nelem_total, ce_w, dice_w, coef, loss_out);
+  return check_launch("bce_dice_sigmoid_finalize");
+}
+int ustrun_bce_dice_sigmoid_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W, float ce_w,
+                                float dice_w, float* workspace, float* coef, float* loss_out, void* stream) {
+  USTRUN_REQUIRE(coef && loss_out, "bce_dice_sigmoid_fwd: null arg");
+  int nparts = 0;
+  int rc = ustrun_bce_dice_sigmoid_partials(logits, target, mask, B, C, H, W, workspace, &nparts, stream);
+  if (rc) return rc;
+  return ustrun_bce_dice_sigmoid_finalize(workspace, nparts, (double)B * C * H * W, ce_w, dice_w, coef, loss_out, stream);
 }
 int ustrun_bce_dice_sigmoid_bwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W, const float* coef,
                                 const float* upstream, float gscale, float* dlogits, int accumulate, void* stream) {

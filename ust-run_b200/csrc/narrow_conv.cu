@@ -39,16 +39,45 @@ k_conv_narrow_in(const T* __restrict__ x, int ldx, const T* __restrict__ wp, con
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int t = 0; t < taps; ++t) {
-      const int hh = h_ + (ks == 3 ? t / 3 : 0) - r, ww = w_ + (ks == 3 ? t % 3 : 0) - r;
-      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-      const T* xp = x + (((long long)b_ * H + hh) * W + ww) * ldx;
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float xv = to_f(xp[ci]);
-        const float4* wv = reinterpret_cast<const float4*>(w_s + (t * Cin + ci) * Cout + cg * 8);
-        const float4 a = wv[0], c = wv[1];
-        acc[0] = fmaf(xv, a.x, acc[0]); acc[1] = fmaf(xv, a.y, acc[1]); acc[2] = fmaf(xv, a.z, acc[2]); acc[3] = fmaf(xv, a.w, acc[3]);
-        acc[4] = fmaf(xv, c.x, acc[4]); acc[5] = fmaf(xv, c.y, acc[5]); acc[6] = fmaf(xv, c.z, acc[6]); acc[7] = fmaf(xv, c.w, acc[7]);
+    if (ks == 3 && Cin <= 4) {
+      // issue all 9*Cin neighbour loads before any FMA (the loads are independent: memory-level parallelism)
+      float xv[9][4];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = h_ + t / 3 - 1, ww = w_ + t % 3 - 1;
+        const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+        const T* xp = x + (((long long)b_ * H + (ok ? hh : h_)) * W + (ok ? ww : w_)) * ldx;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) xv[t][ci] = (ok && ci < Cin) ? to_f(xp[ci < Cin ? ci : 0]) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+          if (ci < Cin) {
+            const float4* wv = reinterpret_cast<const float4*>(w_s + (t * Cin + ci) * Cout + cg * 8);
+            const float4 a = wv[0], c = wv[1];
+            const float v = xv[t][ci];
+            acc[0] = fmaf(v, a.x, acc[0]); acc[1] = fmaf(v, a.y, acc[1]); acc[2] = fmaf(v, a.z, acc[2]); acc[3] = fmaf(v, a.w, acc[3]);
+            acc[4] = fmaf(v, c.x, acc[4]); acc[5] = fmaf(v, c.y, acc[5]); acc[6] = fmaf(v, c.z, acc[6]); acc[7] = fmaf(v, c.w, acc[7]);
+          }
+    } else {
+      for (int t = 0; t < taps; ++t) {
+        const int hh = h_ + (ks == 3 ? t / 3 : 0) - r, ww = w_ + (ks == 3 ? t % 3 : 0) - r;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        const T* xp = x + (((long long)b_ * H + hh) * W + ww) * ldx;
+        float xv[8];
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) xv[ci] = ci < Cin ? to_f(xp[ci < Cin ? ci : 0]) : 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci)
+          if (ci < Cin) {
+            const float4* wv = reinterpret_cast<const float4*>(w_s + (t * Cin + ci) * Cout + cg * 8);
+            const float4 a = wv[0], c = wv[1];
+            const float v = xv[ci];
+            acc[0] = fmaf(v, a.x, acc[0]); acc[1] = fmaf(v, a.y, acc[1]); acc[2] = fmaf(v, a.z, acc[2]); acc[3] = fmaf(v, a.w, acc[3]);
+            acc[4] = fmaf(v, c.x, acc[4]); acc[5] = fmaf(v, c.y, acc[5]); acc[6] = fmaf(v, c.z, acc[6]); acc[7] = fmaf(v, c.w, acc[7]);
+          }
       }
     }
 #pragma unroll
@@ -83,43 +112,76 @@ k_conv_narrow_out(const T* __restrict__ x, int ldx, const T* __restrict__ wp, co
   const int sub = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const long long M = (long long)B * H * W;
   const int r = ks >> 1, chunks = Cin >> 3;
-  for (long long p0 = (long long)blockIdx.x * 32; p0 < M; p0 += (long long)gridDim.x * 32) {
-    const long long p = p0 + slot;
-    const bool ok = p < M;
-    const int w_ = (int)(p % W), h_ = (int)((p / W) % H), b_ = (int)(p / ((long long)W * H));
-    float acc[8];
+  constexpr int UN = 4;                              // pixels per thread per iteration (memory-level parallelism)
+  for (long long p0 = (long long)blockIdx.x * 32 * UN; p0 < M; p0 += (long long)gridDim.x * 32 * UN) {
+    float acc[UN][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (ok) {
-      for (int t = 0; t < taps; ++t) {
-        const int hh = h_ + (ks == 3 ? t / 3 : 0) - r, ww = w_ + (ks == 3 ? t % 3 : 0) - r;
-        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-        const T* xp = x + (((long long)b_ * H + hh) * W + ww) * ldx;
-        for (int c8 = sub; c8 < chunks; c8 += 8) {
-          float xv[8];
-          Vec8<T>::load(xp + c8 * 8, xv);
-          const float* wv = w_s + (t * Cin + c8 * 8) * Cout;
+    for (int u = 0; u < UN; ++u)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 8; ++j) acc[u][j] = 0.f;
+    if (ks == 1 && chunks <= 8) {
+      float xv[UN][8];
 #pragma unroll
-            for (int co = 0; co < 8; ++co)
-              if (co < Cout) acc[co] = fmaf(xv[j], wv[j * Cout + co], acc[co]);
+      for (int u = 0; u < UN; ++u) {
+        const long long p = p0 + u * 32 + slot;
+        if (p < M && sub < chunks) Vec8<T>::load(x + p * ldx + sub * 8, xv[u]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[u][j] = 0.f;
+        }
+      }
+      const float* wv = w_s + (sub < chunks ? sub : 0) * 8 * Cout;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int co = 0; co < 8; ++co)
+          if (co < Cout) {
+            const float wgt = wv[j * Cout + co];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) acc[u][co] = fmaf(xv[u][j], wgt, acc[u][co]);
+          }
+    } else {
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const long long p = p0 + u * 32 + slot;
+        if (p >= M) continue;
+        const int w_ = (int)(p % W), h_ = (int)((p / W) % H), b_ = (int)(p / ((long long)W * H));
+        for (int t = 0; t < taps; ++t) {
+          const int hh = h_ + (ks == 3 ? t / 3 : 0) - r, ww = w_ + (ks == 3 ? t % 3 : 0) - r;
+          if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+          const T* xp = x + (((long long)b_ * H + hh) * W + ww) * ldx;
+          for (int c8 = sub; c8 < chunks; c8 += 8) {
+            float xv[8];
+            Vec8<T>::load(xp + c8 * 8, xv);
+            const float* wv = w_s + (t * Cin + c8 * 8) * Cout;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int co = 0; co < 8; ++co)
+                if (co < Cout) acc[u][co] = fmaf(xv[j], wv[j * Cout + co], acc[u][co]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int co = 0; co < 8; ++co) {
-      acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
-      acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
-      acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 4);
-    }
-    if (ok && sub < Cout) {
-      float v = 0.f;
+    for (int u = 0; u < UN; ++u) {
 #pragma unroll
-      for (int co = 0; co < 8; ++co) v = (co == sub) ? acc[co] : v;
-      if (bias) v += bias[sub];
-      if (y_nchw) y_nchw[(((long long)b_ * Cout + sub) * H + h_) * W + w_] = v;
-      else y[p * ldy + sub] = from_f<T>(v);
+      for (int co = 0; co < 8; ++co)
+        if (co < Cout) {
+          acc[u][co] += __shfl_xor_sync(0xffffffffu, acc[u][co], 1);
+          acc[u][co] += __shfl_xor_sync(0xffffffffu, acc[u][co], 2);
+          acc[u][co] += __shfl_xor_sync(0xffffffffu, acc[u][co], 4);
+        }
+      const long long p = p0 + u * 32 + slot;
+      if (p < M && sub < Cout) {
+        const int w_ = (int)(p % W), h_ = (int)((p / W) % H), b_ = (int)(p / ((long long)W * H));
+        float v = 0.f;
+#pragma unroll
+        for (int co = 0; co < 8; ++co) v = (co == sub) ? acc[u][co] : v;
+        if (bias) v += bias[sub];
+        if (y_nchw) y_nchw[(((long long)b_ * Cout + sub) * H + h_) * W + w_] = v;
+        else y[p * ldy + sub] = from_f<T>(v);
+      }
     }
   }
 }
@@ -144,22 +206,30 @@ k_wgrad_narrow(const T* __restrict__ wide, int ldw, int Cw, const T* __restrict_
 #pragma unroll
     for (int n = 0; n < 8; ++n) acc[j][n] = 0.f;
   if (active) {
-#pragma unroll 4
-    for (long long q = (long long)blockIdx.x * lanes + lane; q < M; q += (long long)gridDim.x * lanes) {
-      const int w_ = (int)(q % W), h_ = (int)((q / W) % H), b_ = (int)(q / ((long long)W * H));
-      const int hh = h_ + dh, ww = w_ + dw;
-      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-      float wv[8];
-      Vec8<T>::load(wide + q * ldw + wg * 8, wv);
-      const T* np = nar + (((long long)b_ * H + (ok ? hh : h_)) * W + (ok ? ww : w_)) * ldn;
+    const long long step = (long long)gridDim.x * lanes;
+    for (long long q0 = (long long)blockIdx.x * lanes + lane; q0 < M; q0 += 4 * step) {
+      float wv[4][8], nv[4][8];
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        if (n < Cn) {
-          const float nv = ok ? to_f(np[n]) : 0.f;
+      for (int u = 0; u < 4; ++u) {              // all loads of 4 pixels first
+        const long long q = q0 + u * step;
+        const bool in = q < M;
+        const long long qq = in ? q : 0;
+        const int w_ = (int)(qq % W), h_ = (int)((qq / W) % H), b_ = (int)(qq / ((long long)W * H));
+        const int hh = h_ + dh, ww = w_ + dw;
+        const bool ok = in && hh >= 0 && hh < H && ww >= 0 && ww < W;
+        Vec8<T>::load(wide + qq * ldw + wg * 8, wv[u]);
+        const T* np = nar + (((long long)b_ * H + (ok ? hh : h_)) * W + (ok ? ww : w_)) * ldn;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j][n] = fmaf(wv[j], nv, acc[j][n]);
-        }
+        for (int n = 0; n < 8; ++n) nv[u][n] = (ok && n < Cn) ? to_f(np[n < Cn ? n : 0]) : 0.f;
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+          if (n < Cn) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j][n] = fmaf(wv[u][j], nv[u][n], acc[j][n]);
+          }
     }
   }
   // sequential rounds: lane l adds into shared memory, lane 0 ends up with the block total
@@ -229,7 +299,7 @@ int narrow_in_launch(const void* x, int ldx, const void* w, const float* bias, v
   const int lanes = 256 / (Cout / 8);
   long long M = (long long)B * H * W;
   long long g = (M + lanes - 1) / lanes;
-  if (g > 592) g = 592;
+  if (g > USTRUN_MAX_PARTS) g = USTRUN_MAX_PARTS;       // 640 blocks x 256 threads; partial-stat rows = blocks
   if (nparts_host) *nparts_host = (int)g;
   k_conv_narrow_in<T><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, B, H, W, Cin, Cout, ks, partials);
   return check_launch("conv_narrow_in");
@@ -238,7 +308,7 @@ template <typename T>
 int narrow_out_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, float* y_nchw, int B, int H, int W, int Cin,
                       int Cout, int ks, cudaStream_t st) {
   long long M = (long long)B * H * W;
-  long long g = (M + 31) / 32;
+  long long g = (M + 127) / 128;
   if (g > 148 * 16) g = 148 * 16;
   k_conv_narrow_out<T><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, y_nchw, B, H, W, Cin, Cout, ks);
   return check_launch("conv_narrow_out");

@@ -58,6 +58,11 @@ _SIGS = {
     "ustrun_pseudo_label_sigmoid": [p] * 8 + [f32, f32, i32, i32, i32, i32] + [p] * 9 + [p],
     "ustrun_mix_to_nhwc": [p, p, p, p, p, i32, i32, i32, i32, i32, i32, p],
     "ustrun_ce_dice_softmax_fwd": [p, p, p, i32, i32, i32, i32, f32, f32, p, p, p, p, p],
+    "ustrun_ce_dice_softmax_partials": [p, p, p, i32, i32, i32, i32, p, ip, p],
+    "ustrun_ce_dice_softmax_finalize": [p, i32, i32, f64, f32, f32, p, p, p, p],
+    "ustrun_reduce_rows": [p, i32, i32, p, p],
+    "ustrun_bce_dice_sigmoid_partials": [p, p, p, i32, i32, i32, i32, p, ip, p],
+    "ustrun_bce_dice_sigmoid_finalize": [p, i32, f64, f32, f32, p, p, p],
     "ustrun_ce_dice_softmax_bwd": [p, p, p, i32, i32, i32, i32, p, p, f32, p, i32, p],
     "ustrun_bce_dice_sigmoid_fwd": [p, p, p, i32, i32, i32, i32, f32, f32, p, p, p, p],
     "ustrun_bce_dice_sigmoid_bwd": [p, p, p, i32, i32, i32, i32, p, p, f32, p, i32, p],

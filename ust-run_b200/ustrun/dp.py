@@ -5,6 +5,8 @@ NVLink/NVSwitch) for the plumbing.  The reference is single-GPU, so
     cuts it into contiguous buckets and all-reduces each bucket on a side stream as soon as the
     LAST loss branch's backward has written all of its tensors (reverse layer order), overlapping
     the remaining backward.  The 1/world averaging is folded into the SGD kernel (``grad_scale``).
+  * loss: the CE/Dice partial sums (3C+1 floats per term) are summed across ranks before the loss
+    finalize kernel (``global_loss``), so G ranks x B images reproduce one device with G*B images.
   * BatchNorm / DSBN statistics: per layer, per pass, a [2*C] fp32 vector (sum, sum of squares;
     backward: sum g', sum g' xhat) is summed across ranks before the finalize kernel, giving
     global-batch BN (G ranks x B images == one device with G*B images).
@@ -81,7 +83,7 @@ class DataParallel:
     """Attach to an ``SSLTrainer`` (``dp=`` argument).  ``sync_bn`` installs the cross-rank
     BatchNorm statistics hook used by every conv+BN op."""
 
-    def __init__(self, group=None, bucket_bytes: int = 32 << 20, sync_bn: bool = True):
+    def __init__(self, group=None, bucket_bytes: int = 32 << 20, sync_bn: bool = True, global_loss: bool = True):
         assert dist.is_initialized(), "init_process_group first (backend nccl on GPUs, gloo in CPU tests)"
         self.group = group
         self.world = dist.get_world_size(group)
@@ -90,6 +92,10 @@ class DataParallel:
         self.buckets: Optional[GradBuckets] = None
         self.branch = 0
         self.sync_bn = sync_bn
+        # global_loss: the (3C+1) CE/Dice partial sums are summed across ranks inside every loss term, so
+        # the step equals the single-device step on the concatenated batch (gradients are then SUMMED);
+        # otherwise each rank has its own loss and gradients are averaged (plain DDP semantics).
+        self.global_loss = global_loss
         if sync_bn and self.world > 1:
             bridge.BN_SYNC = self.sum_across_ranks
             bridge.BN_WORLD = self.world
@@ -129,4 +135,4 @@ class DataParallel:
     def finish_step(self, opt) -> float:
         if self.world > 1:
             self.buckets.flush()
-        return 1.0 / self.world
+        return 1.0 if self.global_loss else 1.0 / self.world

@@ -19,13 +19,35 @@ def as_u8(t: torch.Tensor) -> torch.Tensor:
     return t if t.dtype == torch.uint8 else t.to(torch.uint8)
 
 
-def term_forward(logits, target_u8, mask_u8, branch, ce_w=1.0, dice_w=1.0, class_weight=None):
+def term_forward(logits, target_u8, mask_u8, branch, ce_w=1.0, dice_w=1.0, class_weight=None, allreduce=None, world=1):
     """logits fp32 NCHW [B,C,H,W]; softmax: target/mask uint8 [B,H,W]; sigmoid: uint8 [B,C,H,W].
-    Returns (loss3, coef): loss3 = [ce_w*CE + dice_w*Dice, CE, Dice] (device tensor)."""
+    Returns (loss3, coef): loss3 = [ce_w*CE + dice_w*Dice, CE, Dice] (device tensor).
+    ``allreduce`` (data parallel): callable summing a tensor across ranks in place; the (3C+1) partial
+    sums are reduced across ranks before the finalize kernel, so loss and gradient coefficients are
+    those of the GLOBAL batch (world x local pixels)."""
     L.require_device()
     B, C, H, W = logits.shape
     dev = logits.device
     loss3 = torch.empty(3, dtype=torch.float32, device=dev)
+    if allreduce is not None and world > 1:
+        ncols = 3 * C + 1 if branch == "softmax" else 4
+        ws = torch.empty(L.MAX_PARTS * ncols, dtype=torch.float32, device=dev)
+        sums = torch.empty(ncols, dtype=torch.float32, device=dev)
+        nparts = ctypes.c_int(0)
+        if branch == "softmax":
+            coef = torch.empty(4 * C + 4, dtype=torch.float32, device=dev)
+            _call("ustrun_ce_dice_softmax_partials", _ptr(logits), _ptr(target_u8), _ptr(mask_u8), B, C, H, W, _ptr(ws), ctypes.byref(nparts), _stream())
+            _call("ustrun_reduce_rows", _ptr(ws), nparts.value, ncols, _ptr(sums), _stream())
+            allreduce(sums)
+            _call("ustrun_ce_dice_softmax_finalize", _ptr(sums), 1, C, float(B * H * W) * world, float(ce_w), float(dice_w), _ptr(class_weight),
+                  _ptr(coef), _ptr(loss3), _stream())
+        else:
+            coef = torch.empty(4, dtype=torch.float32, device=dev)
+            _call("ustrun_bce_dice_sigmoid_partials", _ptr(logits), _ptr(target_u8), _ptr(mask_u8), B, C, H, W, _ptr(ws), ctypes.byref(nparts), _stream())
+            _call("ustrun_reduce_rows", _ptr(ws), nparts.value, ncols, _ptr(sums), _stream())
+            allreduce(sums)
+            _call("ustrun_bce_dice_sigmoid_finalize", _ptr(sums), 1, float(B * C * H * W) * world, float(ce_w), float(dice_w), _ptr(coef), _ptr(loss3), _stream())
+        return loss3, coef
     if branch == "softmax":
         ws = torch.empty(L.MAX_PARTS * (3 * C + 1), dtype=torch.float32, device=dev)
         coef = torch.empty(4 * C + 4, dtype=torch.float32, device=dev)

@@ -121,7 +121,10 @@ class SSLTrainer:
     def _branch(self, a, target_u8, mask_u8, weight):
         """forward -> loss -> backward of one loss branch; returns loss3 device tensor."""
         ctx, logits, head_bwd = self._forward(self.model, a, True)
-        loss3, coef = term_forward(logits, target_u8, mask_u8, self.branch)
+        if self.dp is not None and self.dp.global_loss:
+            loss3, coef = term_forward(logits, target_u8, mask_u8, self.branch, allreduce=self.dp.sum_across_ranks, world=self.dp.world)
+        else:
+            loss3, coef = term_forward(logits, target_u8, mask_u8, self.branch)
         dlogits = term_backward(logits, target_u8, mask_u8, self.branch, coef, gscale=weight)
         sink = E.GradSink(provider=self._grad_provider)
         head_bwd(dlogits, sink)
