@@ -91,9 +91,11 @@ int ustrun_bn_act_fwd(const void* x, int ldx, const float* scale, const float* s
 int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const float* mean, const float* rstd,
                          const float* scale, const float* shift, int act, int dtype, long long npix, int C,
                          float* partials, int* nparts_host, void* stream);
-/* dgamma/dbeta (+)= ; coef[3][C] = (gamma*rstd, sum g'/count, sum g' xhat/count) */
+/* dgamma/dbeta (+)= param_grad_scale * (sum g' xhat, sum g'); coef[3][C] = (gamma*rstd, sum g'/count, sum g' xhat/count).
+ * With cross-rank statistics the sums are global: pass param_grad_scale = 1/world so that the later
+ * gradient all-reduce (a sum over ranks) yields the global dgamma/dbeta exactly once. */
 int ustrun_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* rstd,
-                           float* dgamma, float* dbeta, int accumulate, float* coef, void* stream);
+                           float* dgamma, float* dbeta, int accumulate, float param_grad_scale, float* coef, void* stream);
 int ustrun_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, const float* mean, const float* rstd,
                         const float* scale, const float* shift, const float* coef, int act, void* dx, int lddx,
                         int dtype, long long npix, int C, void* stream);

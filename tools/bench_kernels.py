@@ -33,11 +33,16 @@ def act(B, H, W, C):
     a = E.Act.new(B, H, W, C); a.t.normal_(); return a
 
 B, H0 = 8, 384
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+if ONLY == "narrow":
+    layers_skip = True
+else:
+    layers_skip = False
 # ---- tensor-core conv layers of UNet-A ----
 layers = [("inc.3", 64, 64, 1), ("down1.0", 64, 128, 2), ("down1.3", 128, 128, 2), ("down2.0", 128, 256, 4), ("down2.3", 256, 256, 4),
           ("down3.0", 256, 512, 8), ("down3.3", 512, 512, 8), ("down4.0", 512, 1024, 16), ("down4.3", 1024, 1024, 16),
           ("up1.0", 1024, 512, 8), ("up2.0", 512, 256, 4), ("up3.0", 256, 128, 2), ("up4.0", 128, 64, 1)]
-for name, cin, cout, d in layers:
+for name, cin, cout, d in ([] if layers_skip else layers):
     H = H0 // d
     x, y, g = act(B, H, H, cin), act(B, H, H, cout), act(B, H, H, cout)
     w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05

@@ -266,7 +266,7 @@ __global__ void k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __res
 
 __global__ void k_bn_bwd_finalize(const float* __restrict__ partials, int nparts, int C, double count,
                                   const float* __restrict__ gamma, const float* __restrict__ rstd, float* dgamma,
-                                  float* dbeta, int accumulate, float* coef) {
+                                  float* dbeta, int accumulate, float param_grad_scale, float* coef) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
@@ -280,8 +280,8 @@ __global__ void k_bn_bwd_finalize(const float* __restrict__ partials, int nparts
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   }
   if (lane != 0) return;
-  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
-  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + param_grad_scale * (float)s2;
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + param_grad_scale * (float)s1;
   float g = gamma ? gamma[c] : 1.f;
   coef[c] = g * rstd[c];
   coef[C + c] = (float)(s1 / count);
@@ -566,9 +566,9 @@ int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const f
   return check_launch("bn_bwd_reduce");
 }
 int ustrun_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* rstd, float* dgamma,
-                           float* dbeta, int accumulate, float* coef, void* stream) {
+                           float* dbeta, int accumulate, float param_grad_scale, float* coef, void* stream) {
   USTRUN_REQUIRE(partials && nparts > 0 && C > 0 && rstd && coef && count > 0, "bn_bwd_finalize: bad args");
-  k_bn_bwd_finalize<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, rstd, dgamma, dbeta, accumulate, coef);
+  k_bn_bwd_finalize<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, rstd, dgamma, dbeta, accumulate, param_grad_scale, coef);
   return check_launch("bn_bwd_finalize");
 }
 int ustrun_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, const float* mean, const float* rstd, const float* scale,

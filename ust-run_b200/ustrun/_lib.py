@@ -49,7 +49,7 @@ _SIGS = {
     "ustrun_bn_finalize": [p, i32, i32, f64, p, p, p, p, p, p, f32, f32, i32, p, p, p, p, p],
     "ustrun_bn_act_fwd": [p, i32, p, p, i32, p, i32, p, i32, i32, i32, i32, i32, i32, p],
     "ustrun_bn_bwd_reduce": [p, i32, p, i32, p, p, p, p, i32, i32, i64, i32, p, ip, p],
-    "ustrun_bn_bwd_finalize": [p, i32, i32, f64, p, p, p, p, i32, p, p],
+    "ustrun_bn_bwd_finalize": [p, i32, i32, f64, p, p, p, p, i32, f32, p, p],
     "ustrun_bn_bwd_apply": [p, i32, p, i32, p, p, p, p, p, i32, p, i32, i32, i64, i32, p],
     "ustrun_maxpool_bwd": [p, i32, p, i32, p, i32, p, i32, i32, i32, i32, i32, i32, p],
     "ustrun_upsample2x_fwd": [p, i32, p, i32, i32, i32, i32, i32, i32, i32, p],

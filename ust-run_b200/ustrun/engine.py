@@ -327,7 +327,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
             dg, acc_g = sink.get(bn.weight) if bn.weight is not None else (None, 0)
             db, acc_b = sink.get(bn.bias) if bn.bias is not None else (None, 0)
             _call("ustrun_bn_bwd_finalize", _ptr(part), n_parts, cout, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
-                  1 if (acc_g or acc_b) else 0, _ptr(coef), _stream())
+                  1 if (acc_g or acc_b) else 0, 1.0 / world if bn_sync is not None else 1.0, _ptr(coef), _stream())
             draw = raw.like()
             _call("ustrun_bn_bwd_apply", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
                   act, draw.ptr, draw.ld, raw.dtype_code, raw.npix, cout, _stream())
@@ -494,7 +494,7 @@ def batchnorm_only(ctx: Ctx, x: Act, bn):
             dg, a1 = sink.get(bn.weight) if bn.weight is not None else (None, 0)
             db, a2 = sink.get(bn.bias) if bn.bias is not None else (None, 0)
             _call("ustrun_bn_bwd_finalize", _ptr(parts), n_parts, C, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db), 1 if (a1 or a2) else 0,
-                  _ptr(coef), _stream())
+                  1.0 / world if bn_sync is not None else 1.0, _ptr(coef), _stream())
             if x.needs_grad:
                 gx = x.like()
                 _call("ustrun_bn_bwd_apply", G.ptr, G.ld, x.ptr, x.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
