@@ -144,7 +144,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from ustrun.dp import DataParallel
-        dp = DataParallel(sync_bn=not args.no_sync_bn)
+        dp = DataParallel(sync_bn=False if args.no_sync_bn else (args.sync_bn if args.sync_bn != "auto" else True))
     model_name, c, k, H, W, Bl, Bu, branch = WORKLOADS[args.workload]
     E.set_precision(args.precision)
     student, teacher = make_models(model_name, c, k)
@@ -243,7 +243,7 @@ def run_ours(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"{args.workload}: {model_name} {c}x{H}x{W}, {k} classes, {Bl}+{Bu} per GPU, {branch} branch, SSL step",
                        "global_batch": imgs, "parallelism": f"dp{world}", "l2": "working set (GBs of activations per step) >> 126 MB L2; no flush needed",
-                       "sync_bn": bool(world > 1 and not args.no_sync_bn)},
+                       "sync_bn": (False if (world == 1 or args.no_sync_bn) else ("peer" if dp is not None and dp.peer is not None else "nccl"))},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
@@ -316,6 +316,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-sync-bn", action="store_true")
+    ap.add_argument("--sync-bn", default="auto", choices=["auto", "peer", "nccl"], help="cross-rank BN statistics: fused peer-memory kernel or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -108,6 +108,24 @@ int ustrun_upsample2x_fwd(const void* x, int ldx, void* y, int ldy, int dtype, i
 int ustrun_upsample2x_bwd(const void* dy, int lddy, void* dx, int lddx, int dtype, int B, int H, int W, int C,
                           int align_corners, void* stream);
 
+/* ---- BatchNorm finalize fused with the cross-rank reduction over NVLink peer memory ----
+ * peer_bases: HOST array of `world` device pointers, entry r = rank r's symmetric buffer of
+ * ustrun_peer_buffer_bytes() bytes (zero-initialised once, e.g. torch.distributed._symmetric_memory),
+ * mapped into this process.  `seq` must be the same, strictly increasing number on every rank for
+ * each call; counter (uint32, zeroed once) and error (int32) are local device scalars.  One kernel
+ * replaces {partial-row reduction, NCCL all-reduce of 2*C floats, finalize}. */
+long long ustrun_peer_buffer_bytes(void);
+int ustrun_bn_finalize_peer(const float* partials, int nparts, int C, double count_global, const float* gamma, const float* beta,
+                            const float* conv_bias, float* running_mean, float* running_var, long long* num_batches_tracked,
+                            float momentum, float eps, float* scale, float* shift, float* mean, float* rstd,
+                            const void* const* peer_bases, int rank, int world, unsigned int seq, unsigned int* counter,
+                            int* error, void* stream);
+/* dgamma/dbeta receive the LOCAL sums (the gradient all-reduce adds the ranks), coef the global means */
+int ustrun_bn_bwd_finalize_peer(const float* partials, int nparts, int C, double count_global, const float* gamma,
+                                const float* rstd, float* dgamma, float* dbeta, int accumulate, float* coef,
+                                const void* const* peer_bases, int rank, int world, unsigned int seq, unsigned int* counter,
+                                int* error, void* stream);
+
 /* ---- pseudo labels (K12): train.py:649-697, train_mnms.py:595-623 -------------------------- */
 /* softmax branch.  t1,t2,t3 (teacher) and s0 (student, nullable) are fp32 NCHW logits [Bu,C,H,W];
  * box, cut_label, cut_mask are uint8 ([Bu,H,W], [Nc,H,W], [Nc,H,W]); choice int32[Bu].

@@ -69,6 +69,17 @@ template <> struct Vec8<float> {
   }
 };
 
+// linear pixel index -> (b, h, w) with 32-bit arithmetic (64-bit div/mod costs ~100 instructions each;
+// every entry point checks B*H*W < 2^31)
+__device__ __forceinline__ void pix_decomp(long long p, int W, int H, int& b, int& h, int& w) {
+  const unsigned int q = (unsigned int)p;
+  const unsigned int t = q / (unsigned int)W;
+  w = (int)(q - t * (unsigned int)W);
+  const unsigned int bb = t / (unsigned int)H;
+  h = (int)(t - bb * (unsigned int)H);
+  b = (int)bb;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

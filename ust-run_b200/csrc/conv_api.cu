@@ -41,6 +41,7 @@ using namespace ustrun;
 
 #define CHECK_COMMON(name)                                                                                            \
   USTRUN_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, name ": empty shape");                               \
+  USTRUN_REQUIRE((long long)B * H * W < (1LL << 31), name ": B*H*W must be < 2^31 (32-bit pixel indexing)");            \
   USTRUN_REQUIRE(dtype == USTRUN_F32 || dtype == USTRUN_BF16, name ": bad dtype");                                    \
   USTRUN_REQUIRE(impl == USTRUN_IMPL_SIMT || (impl == USTRUN_IMPL_TCGEN05 && dtype == USTRUN_BF16), name ": tcgen05 path is bf16 only")
 

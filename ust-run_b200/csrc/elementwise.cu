@@ -173,9 +173,10 @@ k_bn_act(const T* __restrict__ x, int ldx, const float* __restrict__ scale, cons
   float sc[8], sh[8];
   Vec8<float>::load(scale + cg * 8, sc);
   Vec8<float>::load(shift + cg * 8, sh);
+  const long long pstep = stride / CG;             // stride % CG == 0: no division inside the loop
+  (void)n;
 #pragma unroll 4
-  for (; i < n; i += stride) {
-    const long long p = i / CG;
+  for (long long p = i / CG; p < npix; p += pstep) {
     float v[8];
     Vec8<T>::load(x + p * ldx + cg * 8, v);
 #pragma unroll
@@ -192,11 +193,12 @@ __global__ void k_bn_act_pool(const T* __restrict__ x, int ldx, const float* __r
   int CG = C >> 3, Hp = H >> 1, Wp = W >> 1;
   long long n = (long long)B * Hp * Wp * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long q = i / CG;
-    int wp = (int)(q % Wp);
-    int hp = (int)((q / Wp) % Hp);
-    int b = (int)(q / ((long long)Wp * Hp));
+    const unsigned int iu = (unsigned int)i;
+    const unsigned int qu = iu / (unsigned int)CG;
+    int cg = (int)(iu - qu * (unsigned int)CG);
+    long long q = qu;
+    int wp, hp, b;
+    pix_decomp(q, Wp, Hp, b, hp, wp);
     float sc[8], sh[8], m[8];
     Vec8<float>::load(scale + cg * 8, sc);
     Vec8<float>::load(shift + cg * 8, sh);
@@ -307,9 +309,10 @@ k_bn_bwd_apply(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ld
   Vec8<float>::load(coef + cg * 8, a);
   Vec8<float>::load(coef + C + cg * 8, b);
   Vec8<float>::load(coef + 2 * C + cg * 8, d);
+  const long long pstep = stride / CG;             // stride % CG == 0: no division inside the loop
+  (void)n;
 #pragma unroll 2
-  for (; i < n; i += stride) {
-    const long long p = i / CG;
+  for (long long p = i / CG; p < npix; p += pstep) {
     float gv[8], xv[8], o[8];
     Vec8<T>::load(g + p * ldg + cg * 8, gv);
     Vec8<T>::load(x + p * ldx + cg * 8, xv);
@@ -329,11 +332,12 @@ __global__ void k_maxpool_bwd(const T* __restrict__ y, int ldy, const T* __restr
   int CG = C >> 3, Hp = H >> 1, Wp = W >> 1;
   long long n = (long long)B * Hp * Wp * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long q = i / CG;
-    int wp = (int)(q % Wp);
-    int hp = (int)((q / Wp) % Hp);
-    int b = (int)(q / ((long long)Wp * Hp));
+    const unsigned int iu = (unsigned int)i;
+    const unsigned int qu = iu / (unsigned int)CG;
+    int cg = (int)(iu - qu * (unsigned int)CG);
+    long long q = qu;
+    int wp, hp, b;
+    pix_decomp(q, Wp, Hp, b, hp, wp);
     float v[4][8], dp[8];
     long long p[4];
 #pragma unroll
@@ -390,11 +394,12 @@ __global__ void k_upsample2x_fwd(const T* __restrict__ x, int ldx, T* __restrict
   int CG = C >> 3, Ho = 2 * H, Wo = 2 * W;
   long long n = (long long)B * Ho * Wo * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long q = i / CG;
-    int ow = (int)(q % Wo);
-    int oh = (int)((q / Wo) % Ho);
-    int b = (int)(q / ((long long)Wo * Ho));
+    const unsigned int iu = (unsigned int)i;
+    const unsigned int qu = iu / (unsigned int)CG;
+    int cg = (int)(iu - qu * (unsigned int)CG);
+    long long q = qu;
+    int ow, oh, b;
+    pix_decomp(q, Wo, Ho, b, oh, ow);
     int h0, h1, w0, w1;
     float lh0, lh1, lw0, lw1;
     src_index(oh, H, Ho, align, h0, h1, lh0, lh1);
@@ -417,11 +422,12 @@ __global__ void k_upsample2x_bwd(const T* __restrict__ dy, int lddy, T* __restri
   int CG = C >> 3, Ho = 2 * H, Wo = 2 * W;
   long long n = (long long)B * H * W * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long q = i / CG;
-    int w = (int)(q % W);
-    int h = (int)((q / W) % H);
-    int b = (int)(q / ((long long)W * H));
+    const unsigned int iu = (unsigned int)i;
+    const unsigned int qu = iu / (unsigned int)CG;
+    int cg = (int)(iu - qu * (unsigned int)CG);
+    long long q = qu;
+    int w, h, b;
+    pix_decomp(q, W, H, b, h, w);
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) k_pseudo_label_softmax(PLArgs a) {
   const long long nvec = (long long)a.Bu * a.HW / V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i * V;
-    const int b = (int)(pix / a.HW);
+    const int b = (int)((unsigned int)pix / (unsigned int)a.HW);
     const int hw = (int)(pix - (long long)b * a.HW);
     const size_t lbase = (size_t)b * C * a.HW + hw;
     float x1[V][MAXC], x2[V][MAXC], x3[V][MAXC], xs[V][MAXC];
@@ -148,7 +148,7 @@ __global__ void k_mix_to_nhwc(const float* __restrict__ a, const float* __restri
                               const uint8_t* __restrict__ box, T* __restrict__ dst, int ld, int B, int C, int HW) {
   const long long n = (long long)B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / HW), hw = (int)(i % HW);
+    const int b = (int)((unsigned int)i / (unsigned int)HW), hw = (int)((unsigned int)i - (unsigned int)b * (unsigned int)HW);
     const bool in = box && box[i] != 0;
     const int sb = b_index ? b_index[b] : b;
     for (int c = 0; c < C; ++c) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) k_ce_dice_pass1(const float* __restrict__
   for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
   const long long n = (long long)B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / HW), hw = (int)(i % HW);
+    const int b = (int)((unsigned int)i / (unsigned int)HW), hw = (int)((unsigned int)i - (unsigned int)b * (unsigned int)HW);
     float x[MAXC];
 #pragma unroll
     for (int c = 0; c < C; ++c) x[c] = logits[((size_t)b * C + c) * HW + hw];
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) k_ce_dice_pass2(const float* __restrict__
   const float ce_scale = coef[2 * C];
   const long long n = (long long)B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / HW), hw = (int)(i % HW);
+    const int b = (int)((unsigned int)i / (unsigned int)HW), hw = (int)((unsigned int)i - (unsigned int)b * (unsigned int)HW);
     float x[MAXC];
 #pragma unroll
     for (int c = 0; c < C; ++c) x[c] = logits[((size_t)b * C + c) * HW + hw];

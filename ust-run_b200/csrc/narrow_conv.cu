@@ -35,7 +35,8 @@ k_conv_narrow_in(const T* __restrict__ x, int ldx, const T* __restrict__ wp, con
 #pragma unroll
   for (int j = 0; j < 8; ++j) { csum[j] = 0.f; csq[j] = 0.f; }
   for (long long p = (long long)blockIdx.x * lanes + lane; p < M; p += (long long)gridDim.x * lanes) {
-    const int w_ = (int)(p % W), h_ = (int)((p / W) % H), b_ = (int)(p / ((long long)W * H));
+    int w_, h_, b_;
+    pix_decomp(p, W, H, b_, h_, w_);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -145,7 +146,8 @@ k_conv_narrow_out(const T* __restrict__ x, int ldx, const T* __restrict__ wp, co
       for (int u = 0; u < UN; ++u) {
         const long long p = p0 + u * 32 + slot;
         if (p >= M) continue;
-        const int w_ = (int)(p % W), h_ = (int)((p / W) % H), b_ = (int)(p / ((long long)W * H));
+        int w_, h_, b_;
+    pix_decomp(p, W, H, b_, h_, w_);
         for (int t = 0; t < taps; ++t) {
           const int hh = h_ + (ks == 3 ? t / 3 : 0) - r, ww = w_ + (ks == 3 ? t % 3 : 0) - r;
           if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
@@ -174,7 +176,8 @@ k_conv_narrow_out(const T* __restrict__ x, int ldx, const T* __restrict__ wp, co
         }
       const long long p = p0 + u * 32 + slot;
       if (p < M && sub < Cout) {
-        const int w_ = (int)(p % W), h_ = (int)((p / W) % H), b_ = (int)(p / ((long long)W * H));
+        int w_, h_, b_;
+    pix_decomp(p, W, H, b_, h_, w_);
         float v = 0.f;
 #pragma unroll
         for (int co = 0; co < 8; ++co) v = (co == sub) ? acc[u][co] : v;
@@ -214,7 +217,8 @@ k_wgrad_narrow(const T* __restrict__ wide, int ldw, int Cw, const T* __restrict_
         const long long q = q0 + u * step;
         const bool in = q < M;
         const long long qq = in ? q : 0;
-        const int w_ = (int)(qq % W), h_ = (int)((qq / W) % H), b_ = (int)(qq / ((long long)W * H));
+        int w_, h_, b_;
+        pix_decomp(qq, W, H, b_, h_, w_);
         const int hh = h_ + dh, ww = w_ + dw;
         const bool ok = in && hh >= 0 && hh < H && ww >= 0 && ww < W;
         Vec8<T>::load(wide + qq * ldw + wg * 8, wv[u]);

@@ -56,10 +56,9 @@ k_conv_simt(const T* __restrict__ x, int ldx, const T* __restrict__ wp, const fl
         long long m = m0 + mm;
         float v = 0.f;
         if (k < K && m < M) {
-          int t = k / g.Cin, c = k - t * g.Cin;
-          int w_ = (int)(m % g.W);
-          int h_ = (int)((m / g.W) % g.H);
-          int b_ = (int)(m / ((long long)g.W * g.H));
+          int t = (int)((unsigned)k / (unsigned)g.Cin), c = k - t * g.Cin;
+          int w_, h_, b_;
+          pix_decomp(m, g.W, g.H, b_, h_, w_);
           long long pix;
           if (in_offset(g, b_, h_, w_, t, pix)) v = to_f(x[pix * ldx + c]);
         }
@@ -88,9 +87,8 @@ k_conv_simt(const T* __restrict__ x, int ldx, const T* __restrict__ wp, const fl
     for (int i = 0; i < 4; ++i) {
       long long m = m0 + ty * 4 + i;
       if (m >= M) continue;
-      int w_ = (int)(m % g.W);
-      int h_ = (int)((m / g.W) % g.H);
-      int b_ = (int)(m / ((long long)g.W * g.H));
+      int w_, h_, b_;
+      pix_decomp(m, g.W, g.H, b_, h_, w_);
       long long opix = m;
       int OH = g.H, OW = g.W;
       if (g.scatter_ij >= 0) {
@@ -161,9 +159,8 @@ k_wgrad_simt(const T* __restrict__ a, int lda, const T* __restrict__ bsrc, int l
       float v = 0.f;
       if (p < p_end && n < N) {
         int t = n / Nin, c = n - t * Nin;
-        int w_ = (int)(p % g.W);
-        int h_ = (int)((p / g.W) % g.H);
-        int b_ = (int)(p / ((long long)g.W * g.H));
+        int w_, h_, b_;
+        pix_decomp(p, g.W, g.H, b_, h_, w_);
         long long pix;
         if (in_offset(g, b_, h_, w_, t, pix)) v = to_f(bsrc[pix * ldb + c]);
       }

@@ -66,6 +66,8 @@ _SIGS = {
     "ustrun_ce_dice_softmax_bwd": [p, p, p, i32, i32, i32, i32, p, p, f32, p, i32, p],
     "ustrun_bce_dice_sigmoid_fwd": [p, p, p, i32, i32, i32, i32, f32, f32, p, p, p, p],
     "ustrun_bce_dice_sigmoid_bwd": [p, p, p, i32, i32, i32, i32, p, p, f32, p, i32, p],
+    "ustrun_bn_finalize_peer": [p, i32, i32, f64, p, p, p, p, p, p, f32, f32, p, p, p, p, p, i32, i32, C.c_uint, p, p, p],
+    "ustrun_bn_bwd_finalize_peer": [p, i32, i32, f64, p, p, p, p, i32, p, p, i32, i32, C.c_uint, p, p, p],
     "ustrun_sgd_ema_multi": [p, p, p, i32, f32, f32, f32, f32, f32, i32, i32, p],
 }
 for _name, _args in _SIGS.items():
@@ -77,7 +79,10 @@ lib.ustrun_last_error_string.argtypes = []
 lib.ustrun_conv_wgrad_workspace_bytes.restype = i64
 lib.ustrun_conv_wgrad_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32]
 
-EXPORTS = sorted(list(_SIGS) + ["ustrun_last_error_string", "ustrun_conv_wgrad_workspace_bytes"])
+lib.ustrun_peer_buffer_bytes.restype = i64
+lib.ustrun_peer_buffer_bytes.argtypes = []
+
+EXPORTS = sorted(list(_SIGS) + ["ustrun_last_error_string", "ustrun_conv_wgrad_workspace_bytes", "ustrun_peer_buffer_bytes"])
 
 
 def last_error() -> str:

@@ -79,6 +79,53 @@ class GradBuckets:
         self.works = []
 
 
+class PeerStats:
+    """Symmetric (peer-mapped) buffers for the BatchNorm finalize kernels that reduce their [2*C]
+    statistics across ranks themselves over NVLink (csrc/peer_bn.cu) instead of calling NCCL."""
+
+    def __init__(self, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib as L
+        grp = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(grp), dist.get_rank(grp)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nbytes = int(L.lib.ustrun_peer_buffer_bytes())
+        self.buf = symm.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, grp)
+        self._bases = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seq = 0
+        self._ctypes = ctypes
+        torch.cuda.synchronize()
+        dist.barrier(grp)
+
+    def args(self):
+        """(peer_bases, rank, world, seq, counter, error) for ustrun_bn_*_finalize_peer; every rank
+        issues the same sequence of calls, so the sequence numbers agree."""
+        self.seq += 1
+        c = self._ctypes
+        return (self._bases, self.rank, self.world, self.seq & 0x7FFFFFFF, c.c_void_p(self.counter.data_ptr()), c.c_void_p(self.error.data_ptr()))
+
+    def check(self):
+        if int(self.error.item()) != 0:
+            raise RuntimeError("peer BatchNorm reduction timed out waiting for another rank")
+
+
+class _BNSync:
+    """bridge.BN_SYNC object: callable NCCL fallback + optional fused peer path."""
+
+    def __init__(self, group, peer):
+        self.group, self.peer = group, peer
+
+    def __call__(self, t: torch.Tensor):
+        dist.all_reduce(t, group=self.group)
+
+
 class DataParallel:
     """Attach to an ``SSLTrainer`` (``dp=`` argument).  ``sync_bn`` installs the cross-rank
     BatchNorm statistics hook used by every conv+BN op."""
@@ -96,8 +143,19 @@ class DataParallel:
         # the step equals the single-device step on the concatenated batch (gradients are then SUMMED);
         # otherwise each rank has its own loss and gradients are averaged (plain DDP semantics).
         self.global_loss = global_loss
+        self.peer = None
         if sync_bn and self.world > 1:
-            bridge.BN_SYNC = self.sum_across_ranks
+            # sync_bn="peer" (default on GPUs): finalize kernels reduce over NVLink peer memory themselves;
+            # sync_bn="nccl": one NCCL all-reduce per layer and pass (validation / CPU tests)
+            want_peer = sync_bn == "peer" or (sync_bn is True and torch.cuda.is_available() and dist.get_backend(group) == "nccl")
+            if want_peer:
+                try:
+                    self.peer = PeerStats(group)
+                except Exception as e:          # symmetric memory unavailable on this platform: say so, use NCCL
+                    if sync_bn == "peer":
+                        raise
+                    print(f"[ustrun.dp] peer-memory BatchNorm statistics unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+            bridge.BN_SYNC = _BNSync(group, self.peer)
             bridge.BN_WORLD = self.world
 
     def close(self):

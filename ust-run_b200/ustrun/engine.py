@@ -158,6 +158,7 @@ class Ctx:
         self.tape: List[Callable] = []
         self.bn_sync = bn_sync           # callable(tensor[2*C]) -> None (in-place cross-rank sum) or None
         self.bn_world = 1
+        self.bn_peer = getattr(bn_sync, "peer", None)   # PeerStats: fused finalize + NVLink peer-memory reduction
 
     def backward(self, sink: GradSink):
         for fn in reversed(self.tape):
@@ -282,13 +283,20 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
     stats = torch.empty(4 * cout, dtype=torch.float32, device=dev)      # scale, shift, mean, rstd
     scale, shift, mean, rstd = stats[:cout], stats[cout:2 * cout], stats[2 * cout:3 * cout], stats[3 * cout:]
     count = float(x.npix)
-    if use_batch_stats and ctx.bn_sync is not None:
+    track = bn.track_running_stats and bn.running_mean is not None and training
+    peer = ctx.bn_peer if use_batch_stats else None
+    if use_batch_stats and ctx.bn_sync is not None and peer is None:
         sums = torch.empty(2 * cout, dtype=torch.float32, device=dev)
         _call("ustrun_bn_reduce_partials", _ptr(partials), nparts, cout, _ptr(sums), _stream())
         ctx.bn_sync(sums)
         partials, nparts, count = sums, 1, count * ctx.bn_world
-    track = bn.track_running_stats and bn.running_mean is not None and training
-    _call("ustrun_bn_finalize", _ptr(partials), nparts, cout, count, _ptr(bn.weight), _ptr(bn.bias), _ptr(conv.bias),
+    if peer is not None:
+        _call("ustrun_bn_finalize_peer", _ptr(partials), nparts, cout, count * ctx.bn_world, _ptr(bn.weight), _ptr(bn.bias), _ptr(conv.bias),
+              _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
+              _ptr(bn.num_batches_tracked) if track else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
+              _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), *peer.args(), _stream())
+    else:
+      _call("ustrun_bn_finalize", _ptr(partials), nparts, cout, count, _ptr(bn.weight), _ptr(bn.bias), _ptr(conv.bias),
           _ptr(bn.running_mean) if (track or not use_batch_stats) else None,
           _ptr(bn.running_var) if (track or not use_batch_stats) else None,
           _ptr(bn.num_batches_tracked) if track else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
@@ -303,6 +311,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
             raise NotImplementedError("backward through eval-mode BatchNorm is not part of the SSL step")
         world = ctx.bn_world if ctx.bn_sync is not None else 1
         bn_sync = ctx.bn_sync
+        bn_peer = ctx.bn_peer
 
         def bwd(sink: GradSink):
             G = y.g
@@ -318,15 +327,19 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
             _call("ustrun_bn_bwd_reduce", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), act,
                   raw.dtype_code, raw.npix, cout, _ptr(part), ctypes.byref(np_), _stream())
             n_parts, cnt = np_.value, float(raw.npix)
-            if bn_sync is not None:
+            coef = torch.empty(3 * cout, dtype=torch.float32, device=dev)
+            dg, acc_g = sink.get(bn.weight) if bn.weight is not None else (None, 0)
+            db, acc_b = sink.get(bn.bias) if bn.bias is not None else (None, 0)
+            if bn_peer is not None:
+                _call("ustrun_bn_bwd_finalize_peer", _ptr(part), n_parts, cout, cnt * world, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
+                      1 if (acc_g or acc_b) else 0, _ptr(coef), *bn_peer.args(), _stream())
+            elif bn_sync is not None:
                 sums = torch.empty(2 * cout, dtype=torch.float32, device=dev)
                 _call("ustrun_bn_reduce_partials", _ptr(part), n_parts, cout, _ptr(sums), _stream())
                 bn_sync(sums)
                 part, n_parts, cnt = sums, 1, cnt * world
-            coef = torch.empty(3 * cout, dtype=torch.float32, device=dev)
-            dg, acc_g = sink.get(bn.weight) if bn.weight is not None else (None, 0)
-            db, acc_b = sink.get(bn.bias) if bn.bias is not None else (None, 0)
-            _call("ustrun_bn_bwd_finalize", _ptr(part), n_parts, cout, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
+            if bn_peer is None:
+              _call("ustrun_bn_bwd_finalize", _ptr(part), n_parts, cout, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
                   1 if (acc_g or acc_b) else 0, 1.0 / world if bn_sync is not None else 1.0, _ptr(coef), _stream())
             draw = raw.like()
             _call("ustrun_bn_bwd_apply", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
