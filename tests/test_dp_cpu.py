@@ -131,12 +131,14 @@ def _dp_step_case(rank, world):
     loss = S.masked_term(U.unet_b_forward(st, x[sl], True), t[sl], None, 2, "softmax")
     loss.backward()
     opt = FakeOpt(plist)
-    dp = DataParallel(sync_bn=False, bucket_bytes=4096)
+    assert DataParallel(sync_bn=False, global_loss=True).finish_step.__name__ == 'finish_step'
+    dp = DataParallel(sync_bn=False, global_loss=False, bucket_bytes=4096)     # per-rank losses -> averaged gradients
     dp.begin_step(opt)
     for i in reversed(range(len(plist))):
         dp.on_grad_requested(plist[i], last_branch=True)
         opt.view(i).copy_(plist[i].grad)
     scale = dp.finish_step(opt)
+    assert scale == 0.5
     return opt.flat_grad * scale, [p.grad.clone() for p in plist], opt.offsets
 
 
