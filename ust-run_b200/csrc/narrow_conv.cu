@@ -12,10 +12,11 @@ namespace ustrun {
 constexpr int NARROW_MAX_W = 6144;   // floats of weights kept in shared memory
 
 // y[p][co] = sum_{tap,ci} x[p+tap][ci] * w[co][tap][ci];  K = taps*Cin small, Cout % 8 == 0
-template <typename T>
+template <typename T, int CIN>     // CIN = compile-time input channels for the 3x3 fast path (0: runtime Cin)
 __global__ void __launch_bounds__(256)
 k_conv_narrow_in(const T* __restrict__ x, int ldx, const T* __restrict__ wp, const float* __restrict__ bias, T* __restrict__ y, int ldy,
-                 int B, int H, int W, int Cin, int Cout, int ks, float* __restrict__ partials) {
+                 int B, int H, int W, int Cin_rt, int Cout, int ks, float* __restrict__ partials) {
+  const int Cin = CIN > 0 ? CIN : Cin_rt;
   __shared__ __align__(16) float w_s[NARROW_MAX_W];     // [k][co]
   __shared__ float red[256][16];
   const int taps = ks * ks, K = taps * Cin;
@@ -40,22 +41,25 @@ k_conv_narrow_in(const T* __restrict__ x, int ldx, const T* __restrict__ wp, con
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (ks == 3 && Cin <= 4) {
-      // issue all 9*Cin neighbour loads before any FMA (the loads are independent: memory-level parallelism)
-      float xv[9][4];
+    if (CIN > 0) {
+      // compile-time Cin, 3x3: issue all 9*Cin neighbour loads before any FMA (independent loads)
+      constexpr int CI = CIN > 0 ? CIN : 1;
+      float xv[9][CI];
+      const bool interior = h_ > 0 && h_ < H - 1 && w_ > 0 && w_ < W - 1;
+      const T* xc = x + p * ldx;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const int hh = h_ + t / 3 - 1, ww = w_ + t % 3 - 1;
-        const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-        const T* xp = x + (((long long)b_ * H + (ok ? hh : h_)) * W + (ok ? ww : w_)) * ldx;
+        const int dh = t / 3 - 1, dw = t % 3 - 1;
+        const bool ok = interior || (h_ + dh >= 0 && h_ + dh < H && w_ + dw >= 0 && w_ + dw < W);
+        const T* xp = xc + (ok ? ((long long)dh * W + dw) * ldx : 0);
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) xv[t][ci] = (ok && ci < Cin) ? to_f(xp[ci < Cin ? ci : 0]) : 0.f;
+        for (int ci = 0; ci < CI; ++ci) xv[t][ci] = ok ? to_f(xp[ci]) : 0.f;
       }
 #pragma unroll
       for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci)
-          if (ci < Cin) {
+        for (int ci = 0; ci < CI; ++ci)
+          {
             const float4* wv = reinterpret_cast<const float4*>(w_s + (t * Cin + ci) * Cout + cg * 8);
             const float4 a = wv[0], c = wv[1];
             const float v = xv[t][ci];
@@ -189,75 +193,74 @@ k_conv_narrow_out(const T* __restrict__ x, int ldx, const T* __restrict__ wp, co
   }
 }
 
-// acc[wc][tap][nc] = sum_q wide[q][wc] * narrow[q + sgn*tap][nc];  one row of partial sums per block
-template <typename T>
+// acc[wc][tap][nc] = sum_q wide[q][wc] * narrow[q + sgn*tap][nc];  one row of partial sums per block.
+// A thread owns 8 wide channels x TG taps x CN narrow channels (TG*CN <= 12): the 16-byte wide vector
+// is loaded once per pixel and reused for all its taps.
+template <typename T, int CN, int TG>
 __global__ void __launch_bounds__(256)
-k_wgrad_narrow(const T* __restrict__ wide, int ldw, int Cw, const T* __restrict__ nar, int ldn, int Cn, int ks, int sgn, int B, int H, int W,
+k_wgrad_narrow(const T* __restrict__ wide, int ldw, int Cw, const T* __restrict__ nar, int ldn, int ks, int sgn, int B, int H, int W,
                float* __restrict__ ws) {
-  __shared__ float red[8192];                      // [per][8*Cn] block reduction over the pixel lanes
-  const int taps = ks * ks, WG = Cw >> 3;
-  const int per = WG * taps, lanes = 256 / per;
+  __shared__ float red[8192];                      // [per][8*TG*CN] block reduction over the pixel lanes
+  constexpr int A = TG * CN;
+  const int taps = ks * ks, WG = Cw >> 3, ngroups = taps / TG;
+  const int per = WG * ngroups, lanes = 256 / per;
   const int lane = threadIdx.x / per;
   const bool active = lane < lanes;
   const int idx = threadIdx.x - lane * per;
-  const int wg = idx % WG, t = idx / WG;
-  const int dh = sgn * ((ks == 3 ? t / 3 : 0) - (ks >> 1)), dw = sgn * ((ks == 3 ? t % 3 : 0) - (ks >> 1));
+  const int wg = idx % WG, tg = idx / WG;
   const long long M = (long long)B * H * W;
-  float acc[8][8];
+  float acc[8][A];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int n = 0; n < 8; ++n) acc[j][n] = 0.f;
+    for (int n = 0; n < A; ++n) acc[j][n] = 0.f;
   if (active) {
     const long long step = (long long)gridDim.x * lanes;
-    for (long long q0 = (long long)blockIdx.x * lanes + lane; q0 < M; q0 += 4 * step) {
-      float wv[4][8], nv[4][8];
+#pragma unroll 2
+    for (long long q = (long long)blockIdx.x * lanes + lane; q < M; q += step) {
+      int w_, h_, b_;
+      pix_decomp(q, W, H, b_, h_, w_);
+      float wv[8], nv[A];
+      Vec8<T>::load(wide + q * ldw + wg * 8, wv);
+      const T* nc0 = nar + q * ldn;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {              // all loads of 4 pixels first
-        const long long q = q0 + u * step;
-        const bool in = q < M;
-        const long long qq = in ? q : 0;
-        int w_, h_, b_;
-        pix_decomp(qq, W, H, b_, h_, w_);
-        const int hh = h_ + dh, ww = w_ + dw;
-        const bool ok = in && hh >= 0 && hh < H && ww >= 0 && ww < W;
-        Vec8<T>::load(wide + qq * ldw + wg * 8, wv[u]);
-        const T* np = nar + (((long long)b_ * H + (ok ? hh : h_)) * W + (ok ? ww : w_)) * ldn;
+      for (int tt = 0; tt < TG; ++tt) {
+        const int t = tg * TG + tt;
+        const int dh = sgn * ((ks == 3 ? t / 3 : 0) - (ks >> 1)), dw = sgn * ((ks == 3 ? t % 3 : 0) - (ks >> 1));
+        const bool ok = h_ + dh >= 0 && h_ + dh < H && w_ + dw >= 0 && w_ + dw < W;
+        const T* np = nc0 + (ok ? ((long long)dh * W + dw) * ldn : 0);
 #pragma unroll
-        for (int n = 0; n < 8; ++n) nv[u][n] = (ok && n < Cn) ? to_f(np[n < Cn ? n : 0]) : 0.f;
+        for (int n = 0; n < CN; ++n) nv[tt * CN + n] = ok ? to_f(np[n]) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int n = 0; n < A; ++n)
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
-          if (n < Cn) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j][n] = fmaf(wv[u][j], nv[u][n], acc[j][n]);
-          }
+        for (int j = 0; j < 8; ++j) acc[j][n] = fmaf(wv[j], nv[n], acc[j][n]);
     }
   }
   // sequential rounds: lane l adds into shared memory, lane 0 ends up with the block total
-  const int width = 8 * Cn;
+  constexpr int width = 8 * A;
   for (int l = 0; l < lanes; ++l) {
     if (active && lane == l) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
-          if (n < Cn) {
-            float* p = &red[idx * width + j * Cn + n];
-            *p = (l == 0 ? 0.f : *p) + acc[j][n];
-          }
+        for (int n = 0; n < A; ++n) {
+          float* p = &red[idx * width + j * A + n];
+          *p = (l == 0 ? 0.f : *p) + acc[j][n];
+        }
     }
     __syncthreads();
   }
   if (active && lane == 0) {
-    float* row = ws + (size_t)blockIdx.x * ((size_t)Cw * taps * Cn);
+    float* row = ws + (size_t)blockIdx.x * ((size_t)Cw * taps * CN);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int n = 0; n < 8; ++n)
-        if (n < Cn) row[((size_t)(wg * 8 + j) * taps + t) * Cn + n] = red[idx * width + j * Cn + n];
+      for (int tt = 0; tt < TG; ++tt)
+#pragma unroll
+        for (int n = 0; n < CN; ++n)
+          row[((size_t)(wg * 8 + j) * taps + (tg * TG + tt)) * CN + n] = red[idx * width + j * A + tt * CN + n];
   }
 }
 
@@ -291,9 +294,14 @@ static int narrow_wgrad_grid(long long M, int lanes) {
   if (g > cap) g = cap;
   return (int)(g < 1 ? 1 : g);
 }
-bool narrow_wgrad_ok(int Cw, int Cn, int ks) { return Cn <= 8 && Cw % 8 == 0 && (Cw / 8) * ks * ks <= 128; }
+static int narrow_tg(int Cn, int ks) { return ks == 1 ? 1 : (Cn == 1 ? 9 : 3); }
+bool narrow_wgrad_ok(int Cw, int Cn, int ks) {
+  if (!(Cn >= 1 && Cn <= 4 && Cw % 8 == 0 && (ks == 1 || ks == 3))) return false;
+  const int per = (Cw / 8) * (ks * ks / narrow_tg(Cn, ks));
+  return per <= 128 && per * 8 * narrow_tg(Cn, ks) * Cn <= 8192;
+}
 long long narrow_wgrad_ws_bytes(long long M, int Cw, int Cn, int ks) {
-  const int per = (Cw / 8) * ks * ks, lanes = 256 / per;
+  const int per = (Cw / 8) * (ks * ks / narrow_tg(Cn, ks)), lanes = 256 / per;
   return (long long)narrow_wgrad_grid(M, lanes) * Cw * ks * ks * Cn * (long long)sizeof(float);
 }
 
@@ -305,7 +313,13 @@ int narrow_in_launch(const void* x, int ldx, const void* w, const float* bias, v
   long long g = (M + lanes - 1) / lanes;
   if (g > USTRUN_MAX_PARTS) g = USTRUN_MAX_PARTS;       // 640 blocks x 256 threads; partial-stat rows = blocks
   if (nparts_host) *nparts_host = (int)g;
-  k_conv_narrow_in<T><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, B, H, W, Cin, Cout, ks, partials);
+#define NI_LAUNCH(CI) k_conv_narrow_in<T, CI><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, B, H, W, Cin, Cout, ks, partials)
+  if (ks == 3 && Cin == 1) NI_LAUNCH(1);
+  else if (ks == 3 && Cin == 2) NI_LAUNCH(2);
+  else if (ks == 3 && Cin == 3) NI_LAUNCH(3);
+  else if (ks == 3 && Cin == 4) NI_LAUNCH(4);
+  else NI_LAUNCH(0);
+#undef NI_LAUNCH
   return check_launch("conv_narrow_in");
 }
 template <typename T>
@@ -321,11 +335,19 @@ template <typename T>
 int narrow_wgrad_launch(const void* wide, int ldw, int Cw, const void* nar, int ldn, int Cn, int ks, int sgn, int mode, int B, int H, int W,
                         float* dw, int accumulate, void* workspace, long long ws_bytes, cudaStream_t st) {
   long long M = (long long)B * H * W;
-  const int per = (Cw / 8) * ks * ks, lanes = 256 / per;
+  const int TGv = narrow_tg(Cn, ks);
+  const int per = (Cw / 8) * (ks * ks / TGv), lanes = 256 / per;
   const int grid = narrow_wgrad_grid(M, lanes);
   long long need = narrow_wgrad_ws_bytes(M, Cw, Cn, ks);
   if (!workspace || ws_bytes < need) { set_error("narrow wgrad: workspace too small (%lld < %lld)", ws_bytes, need); return USTRUN_ERR_ARG; }
-  k_wgrad_narrow<T><<<grid, 256, 0, st>>>((const T*)wide, ldw, Cw, (const T*)nar, ldn, Cn, ks, sgn, B, H, W, (float*)workspace);
+#define NW_LAUNCH(CNV, TGV) k_wgrad_narrow<T, CNV, TGV><<<grid, 256, 0, st>>>((const T*)wide, ldw, Cw, (const T*)nar, ldn, ks, sgn, B, H, W, (float*)workspace)
+  if (ks == 1) {
+    switch (Cn) { case 1: NW_LAUNCH(1, 1); break; case 2: NW_LAUNCH(2, 1); break; case 3: NW_LAUNCH(3, 1); break; default: NW_LAUNCH(4, 1); break; }
+  } else if (Cn == 1) NW_LAUNCH(1, 9);
+  else if (Cn == 2) NW_LAUNCH(2, 3);
+  else if (Cn == 3) NW_LAUNCH(3, 3);
+  else NW_LAUNCH(4, 3);
+#undef NW_LAUNCH
   int rc = check_launch("wgrad_narrow");
   if (rc) return rc;
   const int n = Cw * ks * ks * Cn;

@@ -17,6 +17,7 @@
 //
 // Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -119,8 +120,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_m
          ((uint32_t)(128 >> 4) << 24);
 }
 // shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_offset = 0) {
+  uint64_t d = (uint64_t)(base_offset & 7) << 49;   // start address not 1024B-aligned: (addr >> 7) & 7
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
@@ -163,24 +164,32 @@ constexpr int kEpiBar0 = 1, kEpiBar1 = 2;
 constexpr uint32_t kStageA = 128 * 128;        // 128 pixel rows x 128 B
 constexpr uint32_t kStagingBytes = 2 * 16384;
 
-template <int BN> struct FwdCfg {
-  static constexpr uint32_t stageB = BN * 128;
-  static constexpr uint32_t stage = kStageA + stageB;
-  static constexpr int stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr uint32_t smem = stages * stage + kStagingBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
+// ROW mode (3x3 conv, tile = 128 consecutive pixels of ONE image row): a stage holds one (dy, channel chunk)
+// box of 136 pixels starting at w0-1 plus the weights of the three dx taps; the three dx taps are three
+// UMMA descriptors into the SAME box, start address advanced by dx*128 B (one pixel row) with the
+// descriptor's base-offset field = dx.  Activation traffic from L2 drops 3x (the operand that bounds the
+// Cout=64/128 layers at the top of the UNet).
+constexpr uint32_t kRowBoxPixels = 136;
+template <int BN, bool ROW> struct FwdCfg {
+  static constexpr uint32_t stageA = ROW ? kRowBoxPixels * 128 : kStageA;
+  static constexpr uint32_t stageB = (ROW ? 3 : 1) * BN * 128;
+  static constexpr uint32_t stage = stageA + stageB;
+  static constexpr int stages = ROW ? (BN == 64 ? 4 : 3) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int nstaging = (ROW && BN == 128) ? 1 : 2;
+  static constexpr uint32_t smem = stages * stage + nstaging * 16384 + 1024 /*barriers*/ + 1024 /*align slack*/;
 };
 
-template <int BN>
+template <int BN, bool ROW>
 __global__ void __launch_bounds__(256, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
           const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
           const TcConvParams p) {
-  using Cfg = FwdCfg<BN>;
+  using Cfg = FwdCfg<BN, ROW>;
   constexpr int S = Cfg::stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + S * Cfg::stage;
-  uint64_t* full_bar = (uint64_t*)(staging + kStagingBytes);
+  uint64_t* full_bar = (uint64_t*)(staging + Cfg::nstaging * 16384);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -191,7 +200,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   const int cta_j = blockIdx.x / p.n_tiles;
   const int n0 = n_tile * BN;
   const int kchunks = p.Cin >> 6;
-  const int num_kb = p.ntaps * kchunks;
+  const int num_kb = (ROW ? 3 : p.ntaps) * kchunks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0);
@@ -213,6 +222,20 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n) {
         const int txi = mt % p.tiles_w, tyi = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
         const int w0 = txi * p.TW, h0 = tyi * p.TH;
+        if constexpr (ROW) {
+          for (int dy = 0; dy < 3; ++dy)
+            for (int kc = 0; kc < kchunks; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::stage;
+              mbar_expect_tx(&full_bar[stage], Cfg::stage);
+              tma_load_4d(sa, &mapA1, &full_bar[stage], kc * 64, w0 - 1, h0 + dy - 1, b);      // mapA1: box of 136 pixels
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx)
+                tma_load_2d(sa + Cfg::stageA + dx * BN * 128, &mapW, &full_bar[stage], ((dy * 3 + dx) * kchunks + kc) * 64, n0);
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+          continue;
+        }
         for (int tap = 0; tap < p.ntaps; ++tap) {
           int dh = 0, dw = 0;
           const CUtensorMap* mA = &mapA0;
@@ -223,7 +246,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             uint8_t* sa = smem + stage * Cfg::stage;
             mbar_expect_tx(&full_bar[stage], (uint32_t)(p.TH * p.TW * 128) + Cfg::stageB);
             tma_load_4d(sa, mA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, b);
-            tma_load_2d(sa + kStageA, &mapW, &full_bar[stage], (tap * kchunks + kc) * 64, n0);
+            tma_load_2d(sa + Cfg::stageA, &mapW, &full_bar[stage], (tap * kchunks + kc) * 64, n0);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -244,11 +267,22 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::stage);
-          const uint64_t adesc = make_sdesc(sa, 16, 1024);
-          const uint64_t bdesc = make_sdesc(sa + kStageA, 16, 1024);
+          if constexpr (ROW) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)     // 64 channels = 4 x UMMA_K(16); +32 B inside the swizzle row
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int dx = 0; dx < 3; ++dx) {          // three taps out of one box: start += dx pixel rows, base offset = dx
+              const uint64_t adesc = make_sdesc(sa + dx * 128, 16, 1024, dx);
+              const uint64_t bdesc = make_sdesc(sa + Cfg::stageA + dx * BN * 128, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | dx | k) != 0);
+            }
+          } else {
+            const uint64_t adesc = make_sdesc(sa, 16, 1024);
+            const uint64_t bdesc = make_sdesc(sa + Cfg::stageA, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)     // 64 channels = 4 x UMMA_K(16); +32 B inside the swizzle row
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
           tc_commit(&empty_bar[stage]);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
@@ -275,8 +309,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       tc_fence_after();
 #pragma unroll
       for (int c64 = 0; c64 < BN / 64; ++c64, ++chunk_ctr) {
-        uint8_t* stg = staging + (chunk_ctr & 1) * 16384;
-        if (epi_tid == 0) tma_store_wait_read<1>();    // the store that last used this buffer has drained
+        uint8_t* stg = staging + (chunk_ctr % Cfg::nstaging) * 16384;
+        if (epi_tid == 0) tma_store_wait_read<Cfg::nstaging - 1>();    // the store that last used this buffer has drained
         named_bar_sync(kEpiBar0, 128);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -516,6 +550,14 @@ static void pick_tile(int H, int W, int target, bool exact_pow2, int& TW, int& T
   }
 }
 
+static bool row_mode_enabled() {      // USTRUN_TC_ROW=0 disables the row-reuse variant (A/B comparisons)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USTRUN_TC_ROW");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -533,13 +575,13 @@ struct ActView {            // NHWC bf16 view in elements
   long long sw, sh, sb;
 };
 
-template <int BN>
+template <int BN, bool ROW = false>
 static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot, const ActView& out, TcConvParams p, cudaStream_t st) {
-  using Cfg = FwdCfg<BN>;
+  using Cfg = FwdCfg<BN, ROW>;
   CUtensorMap mA[4], mW, mO;
   for (int i = 0; i < 4; ++i) {
     const ActView& v = a[i < nmaps ? i : 0];
-    int rc = make_act_map(&mA[i], v.base, v.C, v.W, v.H, v.B, v.sw, v.sh, v.sb, p.TW, p.TH);
+    int rc = make_act_map(&mA[i], v.base, v.C, v.W, v.H, v.B, v.sw, v.sh, v.sb, (ROW && i == 1) ? (int)kRowBoxPixels : p.TW, p.TH);
     if (rc) return rc;
   }
   int rc = make_w_map(&mW, w, Ktot, p.Cout, BN);
@@ -548,8 +590,8 @@ static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_tc_conv<%d>, %u): %s", BN, Cfg::smem, cudaGetErrorString(e)); return (int)e; }
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<BN, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_tc_conv<%d,%d>, %u): %s", BN, (int)ROW, Cfg::smem, cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
   p.n_tiles = p.Cout / BN;
@@ -558,7 +600,7 @@ static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot
   if (per > p.m_tiles) per = p.m_tiles;
   if (per > USTRUN_MAX_PARTS) per = USTRUN_MAX_PARTS;
   p.ctas_per_n = per;
-  k_tc_conv<BN><<<p.n_tiles * per, 256, Cfg::smem, st>>>(mA[0], mA[1], mA[2], mA[3], mW, mO, p);
+  k_tc_conv<BN, ROW><<<p.n_tiles * per, 256, Cfg::smem, st>>>(mA[0], mA[1], mA[2], mA[3], mW, mO, p);
   return check_launch("k_tc_conv");
 }
 
@@ -569,19 +611,27 @@ int tc_conv_fwd(const void* x, int ldx, const void* w, const float* bias, void* 
   TcConvParams p{};
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.ntaps = ksize * ksize; p.tap_mode = ksize == 3 ? TAP_CONV3 : TAP_NONE;
-  pick_tile(H, W, 128, false, p.TW, p.TH);
+  const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  // row mode: 3x3, N tile <= 128, image rows wide enough that 128-pixel row segments waste < 25 %
+  const bool row = row_mode_enabled() && ksize == 3 && BN <= 128 && W >= 128 && (double)W / (((W + 127) / 128) * 128) >= 0.75;
+  if (row) { p.TW = 128; p.TH = 1; }
+  else pick_tile(H, W, 128, false, p.TW, p.TH);
   p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
   p.m_tiles = B * p.tiles_w * p.tiles_h;
   p.partials = partials; p.bias = bias;
   ActView a{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
   ActView o{y, Cout, W, H, B, ldy, (long long)W * ldy, (long long)H * W * ldy};
-  const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   int nt = Cout / BN, per = num_sms() / nt;
   if (per < 1) per = 1;
   if (per > p.m_tiles) per = p.m_tiles;
   if (per > USTRUN_MAX_PARTS) per = USTRUN_MAX_PARTS;
   if (nparts_host) *nparts_host = per;
   long long Ktot = (long long)p.ntaps * Cin;
+  if (row) {
+    ActView aa[2] = {a, a};
+    if (BN == 128) return launch_fwd<128, true>(aa, 2, w, Ktot, o, p, st);
+    return launch_fwd<64, true>(aa, 2, w, Ktot, o, p, st);
+  }
   if (BN == 256) return launch_fwd<256>(&a, 1, w, Ktot, o, p, st);
   if (BN == 128) return launch_fwd<128>(&a, 1, w, Ktot, o, p, st);
   return launch_fwd<64>(&a, 1, w, Ktot, o, p, st);
