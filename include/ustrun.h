@@ -30,7 +30,7 @@ enum { USTRUN_F32 = 0, USTRUN_BF16 = 1 };
 enum { USTRUN_ACT_NONE = 0, USTRUN_ACT_RELU = 1, USTRUN_ACT_LEAKY = 2 };
 enum { USTRUN_IMPL_SIMT = 0, USTRUN_IMPL_TCGEN05 = 1 };
 /* rows a per-channel partial-sum workspace must provide: float[USTRUN_MAX_PARTS][2][C] */
-#define USTRUN_MAX_PARTS 640
+#define USTRUN_MAX_PARTS 1280
 
 int ustrun_abi_version(void);
 const char* ustrun_last_error_string(void);

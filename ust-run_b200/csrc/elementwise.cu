@@ -565,7 +565,7 @@ int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const f
   int lanes = 256 / (C / 8);
   int grid = (int)((npix + lanes - 1) / lanes);
   if (grid > USTRUN_MAX_PARTS) grid = USTRUN_MAX_PARTS;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148 * 8) grid = 148 * 8;
   *nparts_host = grid;
   DISPATCH_DTYPE(dtype, (k_bn_bwd_reduce<T><<<grid, 256, 256 * 16 * sizeof(float), (cudaStream_t)stream>>>(
                             (const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale, shift, act, npix, C, partials)));

@@ -361,7 +361,7 @@ __global__ void k_reduce_rows(const float* __restrict__ rows, int nrows, int nco
 static inline int loss_grid(long long n) {
   long long b = (n + 255) / 256;
   if (b > USTRUN_MAX_PARTS) b = USTRUN_MAX_PARTS;
-  if (b > 148 * 4) b = 148 * 4;
+  if (b > 148 * 8) b = 148 * 8;
   return (int)(b < 1 ? 1 : b);
 }
 

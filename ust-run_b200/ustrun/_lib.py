@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libustrun_sm100.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 SIMT, TCGEN05 = 0, 1
-MAX_PARTS = 640
+MAX_PARTS = 1280
 OPT_CHUNK = 4096
 
 
