@@ -158,6 +158,7 @@ struct TcConvParams {
   int m_tiles, n_tiles, ctas_per_n;
   float* partials;       // [ctas_per_n][2][Cout] or null
   const float* bias;     // [Cout] or null
+  int row_bo;            // ROW mode: put dx into the descriptor base-offset field
 };
 
 constexpr int kEpiBar0 = 1, kEpiBar1 = 2;
@@ -270,7 +271,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           if constexpr (ROW) {
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {          // three taps out of one box: start += dx pixel rows, base offset = dx
-              const uint64_t adesc = make_sdesc(sa + dx * 128, 16, 1024, dx);
+              const uint64_t adesc = make_sdesc(sa + dx * 128, 16, 1024, p.row_bo ? dx : 0);
               const uint64_t bdesc = make_sdesc(sa + Cfg::stageA + dx * BN * 128, 16, 1024);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -550,13 +551,13 @@ static void pick_tile(int H, int W, int target, bool exact_pow2, int& TW, int& T
   }
 }
 
-static bool row_mode_enabled() {      // USTRUN_TC_ROW=0 disables the row-reuse variant (A/B comparisons)
+static int row_mode() {      // USTRUN_TC_ROW: 0 = off, 1 = descriptor base offset = dx, 2 = base offset 0 (address-based swizzle)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("USTRUN_TC_ROW");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = e ? atoi(e) : 0;
   }
-  return v == 1;
+  return v;
 }
 static int g_num_sms = 0;
 static int num_sms() {
@@ -613,8 +614,8 @@ int tc_conv_fwd(const void* x, int ldx, const void* w, const float* bias, void* 
   p.ntaps = ksize * ksize; p.tap_mode = ksize == 3 ? TAP_CONV3 : TAP_NONE;
   const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   // row mode: 3x3, N tile <= 128, image rows wide enough that 128-pixel row segments waste < 25 %
-  const bool row = row_mode_enabled() && ksize == 3 && BN <= 128 && W >= 128 && (double)W / (((W + 127) / 128) * 128) >= 0.75;
-  if (row) { p.TW = 128; p.TH = 1; }
+  const bool row = row_mode() > 0 && ksize == 3 && BN <= 128 && W >= 128 && (double)W / (((W + 127) / 128) * 128) >= 0.75;
+  if (row) { p.TW = 128; p.TH = 1; p.row_bo = row_mode() == 1 ? 1 : 0; }
   else pick_tile(H, W, 128, false, p.TW, p.TH);
   p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
   p.m_tiles = B * p.tiles_w * p.tiles_h;
