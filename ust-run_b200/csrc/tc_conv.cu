@@ -158,7 +158,6 @@ struct TcConvParams {
   int m_tiles, n_tiles, ctas_per_n;
   float* partials;       // [ctas_per_n][2][Cout] or null
   const float* bias;     // [Cout] or null
-  int row_bo;            // ROW mode: put dx into the descriptor base-offset field
 };
 
 constexpr int kEpiBar0 = 1, kEpiBar1 = 2;
@@ -167,8 +166,8 @@ constexpr uint32_t kStagingBytes = 2 * 16384;
 
 // ROW mode (3x3 conv, tile = 128 consecutive pixels of ONE image row): a stage holds one (dy, channel chunk)
 // box of 136 pixels starting at w0-1 plus the weights of the three dx taps; the three dx taps are three
-// UMMA descriptors into the SAME box, start address advanced by dx*128 B (one pixel row) with the
-// descriptor's base-offset field = dx.  Activation traffic from L2 drops 3x (the operand that bounds the
+// UMMA descriptors into the SAME box, start address advanced by dx*128 B (one pixel row; the 128B swizzle
+// is address-based, so the descriptor base-offset field stays 0 -- measured, tools/diag_row.py).  Activation traffic from L2 drops 3x (the operand that bounds the
 // Cout=64/128 layers at the top of the UNet).
 constexpr uint32_t kRowBoxPixels = 136;
 template <int BN, bool ROW> struct FwdCfg {
@@ -271,7 +270,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           if constexpr (ROW) {
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {          // three taps out of one box: start += dx pixel rows, base offset = dx
-              const uint64_t adesc = make_sdesc(sa + dx * 128, 16, 1024, p.row_bo ? dx : 0);
+              const uint64_t adesc = make_sdesc(sa + dx * 128, 16, 1024);   // swizzle is a function of the smem address bits: base offset stays 0 (verified on B200)
               const uint64_t bdesc = make_sdesc(sa + Cfg::stageA + dx * BN * 128, 16, 1024);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -551,11 +550,11 @@ static void pick_tile(int H, int W, int target, bool exact_pow2, int& TW, int& T
   }
 }
 
-static int row_mode() {      // USTRUN_TC_ROW: 0 = off, 1 = descriptor base offset = dx, 2 = base offset 0 (address-based swizzle)
+static int row_mode() {      // USTRUN_TC_ROW=0 disables the row-reuse variant (A/B comparisons)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("USTRUN_TC_ROW");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 1;
   }
   return v;
 }
@@ -613,9 +612,10 @@ int tc_conv_fwd(const void* x, int ldx, const void* w, const float* bias, void* 
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.ntaps = ksize * ksize; p.tap_mode = ksize == 3 ? TAP_CONV3 : TAP_NONE;
   const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
-  // row mode: 3x3, N tile <= 128, image rows wide enough that 128-pixel row segments waste < 25 %
-  const bool row = row_mode() > 0 && ksize == 3 && BN <= 128 && W >= 128 && (double)W / (((W + 127) / 128) * 128) >= 0.75;
-  if (row) { p.TW = 128; p.TH = 1; p.row_bo = row_mode() == 1 ? 1 : 0; }
+  // row mode: 3x3, N tile <= 128 (the L2-bound layers at the top of the UNet), rows that split into whole
+  // 128-pixel segments (measured on B200: 64->64 @384 222 -> 155 us; with a 75 %-filled last segment it loses)
+  const bool row = row_mode() > 0 && ksize == 3 && BN <= 128 && W % 128 == 0;
+  if (row) { p.TW = 128; p.TH = 1; }
   else pick_tile(H, W, 128, false, p.TW, p.TH);
   p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
   p.m_tiles = B * p.tiles_w * p.tiles_h;
