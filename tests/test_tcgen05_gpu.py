@@ -19,7 +19,7 @@ SHAPES = [  # B, Cin, Cout, H, W
     (1, 192, 320, 16, 16),     # BN=64 path with several n tiles
     (1, 64, 64, 6, 128),       # row mode (3 dx taps from one 136-pixel box), BN=64
     (2, 128, 64, 3, 384),      # row mode, two channel chunks, 3 tiles per row
-    (1, 64, 128, 5, 192),      # row mode with a half-filled second tile (W=192), BN=128
+    (1, 64, 128, 5, 192),      # W=192: not a multiple of 128 -> generic tiles
     (1, 128, 128, 4, 256),     # row mode BN=128
 ]
 
