@@ -21,6 +21,9 @@ SHAPES = [  # B, Cin, Cout, H, W
     (2, 128, 64, 3, 384),      # row mode, two channel chunks, 3 tiles per row
     (1, 64, 128, 5, 192),      # W=192: not a multiple of 128 -> generic tiles
     (1, 128, 128, 4, 256),     # row mode BN=128
+    (1, 64, 64, 4, 96),        # row-mode wgrad with 48-pixel segments
+    (1, 128, 64, 4, 48),       # row-mode wgrad, swapped operands (Cout=64 < Cin)
+    (1, 256, 256, 24, 24),     # row-mode wgrad, one zero-padded 32-pixel segment per row
 ]
 
 

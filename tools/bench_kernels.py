@@ -13,8 +13,10 @@ torch.manual_seed(0)
 E.set_precision("bf16")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-def timeit(fn, iters=5):
+def timeit(fn, iters=int(os.environ.get('USTRUN_BENCH_ITERS', '5'))):
     fn(); torch.cuda.synchronize()
+    if iters == 0:          # profiling mode (ncu): one launch per kernel
+        return 1.0
     ts = []
     for _ in range(iters):
         flush.zero_()
@@ -42,6 +44,9 @@ else:
 layers = [("inc.3", 64, 64, 1), ("down1.0", 64, 128, 2), ("down1.3", 128, 128, 2), ("down2.0", 128, 256, 4), ("down2.3", 256, 256, 4),
           ("down3.0", 256, 512, 8), ("down3.3", 512, 512, 8), ("down4.0", 512, 1024, 16), ("down4.3", 1024, 1024, 16),
           ("up1.0", 1024, 512, 8), ("up2.0", 512, 256, 4), ("up3.0", 256, 128, 2), ("up4.0", 128, 64, 1)]
+_sel = os.environ.get("USTRUN_BENCH_LAYERS", "")
+if _sel:
+    layers = [l for l in layers if l[0] in _sel.split(",")]
 for name, cin, cout, d in ([] if layers_skip else layers):
     H = H0 // d
     x, y, g = act(B, H, H, cin), act(B, H, H, cout), act(B, H, H, cout)

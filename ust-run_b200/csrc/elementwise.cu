@@ -77,17 +77,31 @@ __global__ void k_nhwc_to_nchw(const T* __restrict__ src, float* __restrict__ ds
   }
 }
 
+// OIHW fp32 -> wf[co][tap][ci] and wd[ci][taps-1-tap][co] (flipped, transposed: the dgrad operand).
+// One block = a 32(co) x 32(ci) x taps tile staged in shared memory so that the fp32 reads (runs of
+// 32*taps floats) and both packed writes (32 consecutive ci / co) are coalesced.
 template <typename T>
-__global__ void k_pack_conv(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cout, int Cin, int taps) {
-  long long n = (long long)Cout * Cin * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int t = (int)(i % taps);
-    int ci = (int)((i / taps) % Cin);
-    int co = (int)(i / ((long long)taps * Cin));
-    float v = w[i];                                            // OIHW: ((co*Cin+ci)*taps + t)
-    if (wf) wf[((size_t)co * taps + t) * Cin + ci] = from_f<T>(v);
-    if (wd) wd[((size_t)ci * taps + (taps - 1 - t)) * Cout + co] = from_f<T>(v);
+__global__ void __launch_bounds__(256)
+k_pack_conv(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cout, int Cin, int taps) {
+  extern __shared__ float tile[];                      // [32 co][32 ci][taps] (+1 pad per co row)
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+  const int nco = min(32, Cout - co0), nci = min(32, Cin - ci0);
+  const int row = 32 * taps + 1;
+  for (int i = threadIdx.x; i < nco * nci * taps; i += 256) {
+    const int co = i / (nci * taps), r = i - co * (nci * taps);          // r = ci*taps + t, contiguous in w
+    tile[co * row + r] = w[((size_t)(co0 + co) * Cin + ci0) * taps + r];
   }
+  __syncthreads();
+  if (wf)
+    for (int i = threadIdx.x; i < nco * taps * nci; i += 256) {
+      const int ci = i % nci, t = (i / nci) % taps, co = i / (nci * taps);
+      wf[((size_t)(co0 + co) * taps + t) * Cin + ci0 + ci] = from_f<T>(tile[co * row + ci * taps + t]);
+    }
+  if (wd)
+    for (int i = threadIdx.x; i < nci * taps * nco; i += 256) {
+      const int co = i % nco, t = (i / nco) % taps, ci = i / (nco * taps);
+      wd[((size_t)(ci0 + ci) * taps + (taps - 1 - t)) * Cout + co0 + co] = from_f<T>(tile[co * row + ci * taps + t]);
+    }
 }
 // ConvTranspose2d weight [Cin][Cout][2][2]
 template <typename T>
@@ -475,12 +489,42 @@ __global__ void k_channel_sum_partial(const T* __restrict__ x, int ldx, long lon
     part[(size_t)blockIdx.x * C + c] = t;
   }
 }
+// 128-bit variant: a thread owns channel group tid % (C/8); requires C % 8 == 0, ld % 8 == 0, 256 % (C/8) == 0
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_channel_sum_partial_v8(const T* __restrict__ x, int ldx, long long npix, int C, float* __restrict__ part) {
+  __shared__ float sm[256][9];
+  const int CG = C >> 3, tid = threadIdx.x;
+  const int cg = tid % CG, lanes = 256 / CG;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 4
+  for (long long p = (long long)blockIdx.x * lanes + tid / CG; p < npix; p += (long long)gridDim.x * lanes) {
+    float v[8];
+    Vec8<T>::load(x + p * ldx + cg * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sm[tid][k] = acc[k];
+  __syncthreads();
+  for (int o = tid; o < C; o += 256) {
+    const int g = o >> 3, k = o & 7;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += sm[l * CG + g][k];
+    part[(size_t)blockIdx.x * C + o] = s;
+  }
+}
+// one warp per channel: lanes stride over the partial rows
 __global__ void k_channel_sum_final(const float* __restrict__ part, int nparts, int C, float* out, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0;
-  for (int r = 0; r < nparts; ++r) s += (double)part[(size_t)r * C + c];
-  out[c] = (accumulate ? out[c] : 0.f) + (float)s;
+  for (int r = lane; r < nparts; r += 32) s += (double)part[(size_t)r * C + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[c] = (accumulate ? out[c] : 0.f) + (float)s;
 }
 
 }  // namespace ustrun
@@ -515,8 +559,10 @@ int ustrun_nhwc_to_nchw(const void* src, int dtype, int ld_src, float* dst, int 
 }
 int ustrun_pack_conv_weight(const float* w, void* wf, void* wd, int dtype, int Cout, int Cin, int ksize, void* stream) {
   USTRUN_REQUIRE(w && (wf || wd) && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), "pack_conv_weight: bad args");
-  long long n = (long long)Cout * Cin * ksize * ksize;
-  DISPATCH_DTYPE(dtype, (k_pack_conv<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (T*)wf, (T*)wd, Cout, Cin, ksize * ksize)));
+  const int taps = ksize * ksize;
+  dim3 grid(ceil_div(Cout, 32), ceil_div(Cin, 32));
+  const size_t smem = (size_t)32 * (32 * taps + 1) * sizeof(float);
+  DISPATCH_DTYPE(dtype, (k_pack_conv<T><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (T*)wf, (T*)wd, Cout, Cin, taps)));
   return check_launch("pack_conv_weight");
 }
 int ustrun_pack_convT_weight(const float* w, void* wf, void* wd, int dtype, int Cin, int Cout, void* stream) {
@@ -610,11 +656,20 @@ int ustrun_upsample2x_bwd(const void* dy, int lddy, void* dx, int lddx, int dtyp
 }
 int ustrun_channel_sum(const void* x, int ldx, int dtype, long long npix, int C, float* out, int accumulate, float* workspace, void* stream) {
   USTRUN_REQUIRE(x && out && workspace && npix > 0 && C > 0, "channel_sum: bad args");
-  int parts = (int)((npix + 63) / 64);
-  if (parts > USTRUN_MAX_PARTS) parts = USTRUN_MAX_PARTS;
-  dim3 grid(parts, ceil_div(C, 32)), block(32, 8);
-  DISPATCH_DTYPE(dtype, (k_channel_sum_partial<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, ldx, npix, C, workspace)));
-  k_channel_sum_final<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(workspace, parts, C, out, accumulate);
+  int parts;
+  if (C % 8 == 0 && ldx % 8 == 0 && (C / 8) <= 256 && 256 % (C / 8) == 0) {
+    const int lanes = 256 / (C / 8);
+    parts = (int)((npix + 4LL * lanes - 1) / (4LL * lanes));          // >= 4 pixels per thread
+    if (parts > 148 * 6) parts = 148 * 6;
+    if (parts < 1) parts = 1;
+    DISPATCH_DTYPE(dtype, (k_channel_sum_partial_v8<T><<<parts, 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, npix, C, workspace)));
+  } else {
+    parts = (int)((npix + 63) / 64);
+    if (parts > USTRUN_MAX_PARTS) parts = USTRUN_MAX_PARTS;
+    dim3 grid(parts, ceil_div(C, 32)), block(32, 8);
+    DISPATCH_DTYPE(dtype, (k_channel_sum_partial<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, ldx, npix, C, workspace)));
+  }
+  k_channel_sum_final<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(workspace, parts, C, out, accumulate);
   return check_launch("channel_sum");
 }
 

@@ -102,6 +102,94 @@ k_conv_narrow_in(const T* __restrict__ x, int ldx, const T* __restrict__ wp, con
   }
 }
 
+// Pixel-quad variant of the narrow-K convolution (compile-time Cin <= 4, ks in {1,3}, W % 4 == 0): a thread
+// owns 8 output channels of FOUR consecutive pixels of one image row, so every weight vector read from
+// shared memory (2 x LDS.128) feeds 32 FMAs and the 3 x 6 input window is loaded once for the quad.
+// FMA-bound at ~20 us for the 1 -> 64 first conv of cfg2; the 16-byte stores of the 8 threads of a pixel
+// form one full 128-byte line.
+template <typename T, int CIN, int KS>
+__global__ void __launch_bounds__(256, KS == 1 ? 2 : 1)
+k_conv_narrow_quad(const T* __restrict__ x, int ldx, const T* __restrict__ wp, const float* __restrict__ bias, T* __restrict__ y, int ldy,
+                   int B, int H, int W, int Cout, float* __restrict__ partials) {
+  constexpr int TAPS = KS * KS, K = TAPS * CIN, R = KS >> 1, WIN = 4 + 2 * R;
+  extern __shared__ __align__(16) float nq_smem[];     // w_s[K][Cout], then red[256][16] when partials
+  float* w_s = nq_smem;
+  for (int i = threadIdx.x; i < K * Cout; i += 256) {
+    const int k = i / Cout, co = i - k * Cout;
+    w_s[i] = to_f(wp[(size_t)co * K + k]);
+  }
+  __syncthreads();
+  const int CG = Cout >> 3, pgs = 256 / CG;
+  const int cg = threadIdx.x % CG, pg = threadIdx.x / CG;
+  const int Wq = W >> 2;
+  const long long nquads = (long long)B * H * Wq;
+  float bs[8], csum[8], csq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { bs[j] = bias ? bias[cg * 8 + j] : 0.f; csum[j] = 0.f; csq[j] = 0.f; }
+  for (long long q = (long long)blockIdx.x * pgs + pg; q < nquads; q += (long long)gridDim.x * pgs) {
+    int wq, h_, b_;
+    pix_decomp(q, Wq, H, b_, h_, wq);
+    const int w0 = wq * 4;
+    float acc[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[u][j] = 0.f;
+    // one window row (WIN x CIN values) live at a time; the next row's loads are issued before this row's FMAs
+    float xw[2][WIN][CIN];
+    auto load_row = [&](int dy, float (&dst)[WIN][CIN]) {
+      const int hh = h_ + dy - R;
+      const bool hok = hh >= 0 && hh < H;
+      const T* rowp = x + ((long long)(b_ * H + (hok ? hh : h_)) * W) * ldx;
+#pragma unroll
+      for (int c = 0; c < WIN; ++c) {
+        const int ww = w0 + c - R;
+        const bool ok = hok && ww >= 0 && ww < W;
+        const T* xp = rowp + (long long)(ok ? ww : w0) * ldx;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) dst[c][ci] = ok ? to_f(xp[ci]) : 0.f;
+      }
+    };
+    load_row(0, xw[0]);
+#pragma unroll
+    for (int dy = 0; dy < KS; ++dy) {
+      if (dy + 1 < KS) load_row(dy + 1, xw[(dy + 1) & 1]);
+#pragma unroll
+      for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float4* wv = reinterpret_cast<const float4*>(w_s + ((dy * KS + dx) * CIN + ci) * Cout + cg * 8);
+          const float4 a = wv[0], c = wv[1];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float v = xw[dy & 1][u + dx][ci];
+            acc[u][0] = fmaf(v, a.x, acc[u][0]); acc[u][1] = fmaf(v, a.y, acc[u][1]); acc[u][2] = fmaf(v, a.z, acc[u][2]); acc[u][3] = fmaf(v, a.w, acc[u][3]);
+            acc[u][4] = fmaf(v, c.x, acc[u][4]); acc[u][5] = fmaf(v, c.y, acc[u][5]); acc[u][6] = fmaf(v, c.z, acc[u][6]); acc[u][7] = fmaf(v, c.w, acc[u][7]);
+          }
+        }
+    }
+    T* yp = y + ((long long)(b_ * H + h_) * W + w0) * ldy + cg * 8;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { csum[j] += acc[u][j]; csq[j] = fmaf(acc[u][j], acc[u][j], csq[j]); acc[u][j] += bs[j]; }
+      Vec8<T>::store(yp + (long long)u * ldy, acc[u]);
+    }
+  }
+  if (partials) {
+    float* red = w_s + K * Cout;                       // [256][16]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = csum[j]; red[threadIdx.x * 16 + 8 + j] = csq[j]; }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * Cout; o += 256) {
+      const int which = o / Cout, c = o - which * Cout;
+      float s = 0.f;
+      for (int l = 0; l < pgs; ++l) s += red[(l * CG + (c >> 3)) * 16 + which * 8 + (c & 7)];
+      partials[(size_t)blockIdx.x * 2 * Cout + o] = s;
+    }
+  }
+}
+
 // Cout <= 8 outputs per pixel, Cin % 8 == 0: 8 threads per pixel each own one 16-byte channel chunk
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -193,11 +281,64 @@ k_conv_narrow_out(const T* __restrict__ x, int ldx, const T* __restrict__ wp, co
   }
 }
 
+// 1x1 logits head (Cin <= 64, compile-time COUT <= 4, H*W % 4 == 0), fp32 NCHW output: 8 threads share a
+// pixel (one 16-byte channel chunk each, weights in registers), a thread handles 4 CONSECUTIVE pixels so the
+// class planes are written with 16-byte stores; 3 xor-shuffles reduce the 8 chunk partials.
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256)
+k_head1x1_nchw(const T* __restrict__ x, int ldx, const T* __restrict__ wp, const float* __restrict__ bias, float* __restrict__ y_nchw,
+               long long M, int HW, int Cin) {
+  const int sub = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const int chunks = Cin >> 3;
+  float wreg[8][COUT];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) wreg[j][co] = sub < chunks ? to_f(wp[(size_t)co * Cin + sub * 8 + j]) : 0.f;
+  float bs[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) bs[co] = bias ? bias[co] : 0.f;
+  for (long long p0 = (long long)blockIdx.x * 128 + slot * 4; p0 < M; p0 += (long long)gridDim.x * 128) {
+    float xv[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (sub < chunks) Vec8<T>::load(x + (p0 + u) * ldx + sub * 8, xv[u]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[u][j] = 0.f;
+      }
+    }
+    float acc[4][COUT];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(xv[u][j], wreg[j][co], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        acc[u][co] = a;
+      }
+    if (sub < COUT) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      float b = 0.f;
+#pragma unroll
+      for (int co = 0; co < COUT; ++co)
+        if (co == sub) { o = make_float4(acc[0][co], acc[1][co], acc[2][co], acc[3][co]); b = bs[co]; }
+      o.x += b; o.y += b; o.z += b; o.w += b;
+      const long long img = p0 / HW, pin = p0 - img * HW;
+      *reinterpret_cast<float4*>(y_nchw + (img * COUT + sub) * HW + pin) = o;
+    }
+  }
+}
+
 // acc[wc][tap][nc] = sum_q wide[q][wc] * narrow[q + sgn*tap][nc];  one row of partial sums per block.
 // A thread owns 8 wide channels x TG taps x CN narrow channels (TG*CN <= 12): the 16-byte wide vector
 // is loaded once per pixel and reused for all its taps.
 template <typename T, int CN, int TG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_wgrad_narrow(const T* __restrict__ wide, int ldw, int Cw, const T* __restrict__ nar, int ldn, int ks, int sgn, int B, int H, int W,
                float* __restrict__ ws) {
   __shared__ float red[8192];                      // [per][8*TG*CN] block reduction over the pixel lanes
@@ -288,9 +429,8 @@ bool narrow_in_ok(int Cin, int Cout, int ks) {
 }
 bool narrow_out_ok(int Cin, int Cout, int ks) { return Cout <= 8 && Cin % 8 == 0 && Cin * ks * ks * Cout <= NARROW_MAX_W; }
 static int narrow_wgrad_grid(long long M, int lanes) {
-  long long g = (M + lanes - 1) / lanes;          // aim for ~8K pixel lanes in flight
-  long long cap = (8192 + lanes - 1) / lanes;
-  if (cap > 148 * 16) cap = 148 * 16;
+  long long g = (M + lanes - 1) / lanes;          // exactly one wave: 2 resident blocks per SM (__launch_bounds__(256, 2))
+  const long long cap = 148 * 2;
   if (g > cap) g = cap;
   return (int)(g < 1 ? 1 : g);
 }
@@ -305,27 +445,48 @@ long long narrow_wgrad_ws_bytes(long long M, int Cw, int Cn, int ks) {
   return (long long)narrow_wgrad_grid(M, lanes) * Cw * ks * ks * Cn * (long long)sizeof(float);
 }
 
+template <typename T, int CIN, int KS>
+static int narrow_quad_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cout,
+                              float* partials, int* nparts_host, cudaStream_t st) {
+  const int pgs = 256 / (Cout / 8);
+  const long long nquads = (long long)B * H * (W / 4);
+  long long g = (nquads + pgs - 1) / pgs;
+  if (g > 148 * 8) g = 148 * 8;                          // <= USTRUN_MAX_PARTS partial-stat rows
+  if (nparts_host) *nparts_host = (int)g;
+  const size_t smem = ((size_t)KS * KS * CIN * Cout + (partials ? 256 * 16 : 0)) * sizeof(float);
+  k_conv_narrow_quad<T, CIN, KS><<<(int)g, 256, smem, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, B, H, W, Cout, partials);
+  return check_launch("conv_narrow_quad");
+}
+
 template <typename T>
 int narrow_in_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ks,
                      float* partials, int* nparts_host, cudaStream_t st) {
+  if (W % 4 == 0 && Cin >= 1 && Cin <= 4 && Cout <= 256 && ((size_t)ks * ks * Cin * Cout + 256 * 16) * sizeof(float) <= 48 * 1024) {
+#define NQ(CI, KSV) return narrow_quad_launch<T, CI, KSV>(x, ldx, w, bias, y, ldy, B, H, W, Cout, partials, nparts_host, st)
+    if (ks == 3) { switch (Cin) { case 1: NQ(1, 3); case 2: NQ(2, 3); case 3: NQ(3, 3); default: NQ(4, 3); } }
+    else { switch (Cin) { case 1: NQ(1, 1); case 2: NQ(2, 1); case 3: NQ(3, 1); default: NQ(4, 1); } }
+#undef NQ
+  }
   const int lanes = 256 / (Cout / 8);
   long long M = (long long)B * H * W;
   long long g = (M + lanes - 1) / lanes;
-  if (g > USTRUN_MAX_PARTS) g = USTRUN_MAX_PARTS;       // 640 blocks x 256 threads; partial-stat rows = blocks
+  if (g > USTRUN_MAX_PARTS) g = USTRUN_MAX_PARTS;       // partial-stat rows = blocks
   if (nparts_host) *nparts_host = (int)g;
-#define NI_LAUNCH(CI) k_conv_narrow_in<T, CI><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, B, H, W, Cin, Cout, ks, partials)
-  if (ks == 3 && Cin == 1) NI_LAUNCH(1);
-  else if (ks == 3 && Cin == 2) NI_LAUNCH(2);
-  else if (ks == 3 && Cin == 3) NI_LAUNCH(3);
-  else if (ks == 3 && Cin == 4) NI_LAUNCH(4);
-  else NI_LAUNCH(0);
-#undef NI_LAUNCH
+  k_conv_narrow_in<T, 0><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, B, H, W, Cin, Cout, ks, partials);
   return check_launch("conv_narrow_in");
 }
 template <typename T>
 int narrow_out_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, float* y_nchw, int B, int H, int W, int Cin,
                       int Cout, int ks, cudaStream_t st) {
   long long M = (long long)B * H * W;
+  if (ks == 1 && y_nchw && Cout <= 4 && Cin <= 64 && (H * W) % 4 == 0) {
+    long long g = (M + 127) / 128;
+    if (g > 148 * 8) g = 148 * 8;
+#define HL(CO) k_head1x1_nchw<T, CO><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, y_nchw, M, H * W, Cin)
+    switch (Cout) { case 1: HL(1); break; case 2: HL(2); break; case 3: HL(3); break; default: HL(4); break; }
+#undef HL
+    return check_launch("head1x1_nchw");
+  }
   long long g = (M + 127) / 128;
   if (g > 148 * 16) g = 148 * 16;
   k_conv_narrow_out<T><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, y_nchw, B, H, W, Cin, Cout, ks);

@@ -193,25 +193,49 @@ k_wgrad_simt(const T* __restrict__ a, int lda, const T* __restrict__ bsrc, int l
   }
 }
 
-// dw[(m*Nin + c)*taps + t] (+)= sum_s ws[s][m][t*Nin + c]   (threads walk ws order: coalesced reads of every split)
-__global__ void k_wgrad_reduce(const float* __restrict__ ws, int splits, int Mo, int Nin, int taps, float* __restrict__ dw, int accumulate) {
-  long long n = (long long)Mo * Nin * taps;
-  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(j % Nin);
-    int t = (int)((j / Nin) % taps);
-    int m = (int)(j / ((long long)taps * Nin));
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[(size_t)k * n + j];
-    size_t o = ((size_t)m * Nin + c) * taps + t;
-    dw[o] = (accumulate ? dw[o] : 0.f) + s;
+// dw[(m*Nin + c)*taps + t] (+)= sum_s ws[s][m][t*Nin + c].  A block owns (m, 32 consecutive c): the split
+// partials are read as 128-byte runs along c for every tap, summed, transposed through shared memory and
+// written (read-modify-write when accumulating) as one contiguous run of 32*taps floats of the OIHW tensor.
+__global__ void __launch_bounds__(128)
+k_wgrad_reduce(const float* __restrict__ ws, int splits, int Mo, int Nin, int taps, float* __restrict__ dw, int accumulate, int swapped) {
+  __shared__ float tile[9][33];
+  const int cchunks = (Nin + 31) >> 5;
+  const long long n = (long long)Mo * Nin * taps;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (long long item = blockIdx.x; item < (long long)Mo * cchunks; item += gridDim.x) {
+    const int m = (int)(item / cchunks), c0 = (int)(item - (long long)m * cchunks) * 32;
+    const int nc = min(32, Nin - c0);
+    for (int t = wrp; t < taps; t += 4) {
+      float s = 0.f;
+      if (lane < nc) {
+        const float* src = ws + ((size_t)m * taps + t) * Nin + c0 + lane;
+        for (int k = 0; k < splits; ++k) s += src[(size_t)k * n];
+      }
+      tile[t][lane] = s;
+    }
+    __syncthreads();
+    if (!swapped) {
+      float* dst = dw + ((size_t)m * Nin + c0) * taps;
+      for (int i = threadIdx.x; i < nc * taps; i += 128) {
+        const int c = i / taps, t = i - c * taps;
+        dst[i] = (accumulate ? dst[i] : 0.f) + tile[t][c];
+      }
+    } else {                                       // ws rows are input channels: dw[(c*Mo + m)*taps + t]
+      for (int i = threadIdx.x; i < nc * taps; i += 128) {
+        const int c = i / taps, t = i - c * taps;
+        float* d = dw + ((size_t)(c0 + c) * Mo + m) * taps + t;
+        *d = (accumulate ? *d : 0.f) + tile[t][c];
+      }
+    }
+    __syncthreads();
   }
 }
 
-int launch_wgrad_reduce(const float* ws, int splits, int Mo, int Nin, int taps, float* dw, int accumulate, cudaStream_t st) {
-  long long n = (long long)Mo * Nin * taps;
-  int rb = (int)((n + 255) / 256);
-  if (rb > 148 * 8) rb = 148 * 8;
-  k_wgrad_reduce<<<rb, 256, 0, st>>>(ws, splits, Mo, Nin, taps, dw, accumulate);
+int launch_wgrad_reduce(const float* ws, int splits, int Mo, int Nin, int taps, float* dw, int accumulate, cudaStream_t st, int swapped) {
+  if (taps > 9) { set_error("wgrad_reduce: taps > 9"); return USTRUN_ERR_ARG; }
+  long long items = (long long)Mo * ((Nin + 31) / 32);
+  int rb = (int)(items < 148 * 16 ? items : 148 * 16);
+  k_wgrad_reduce<<<rb, 128, 0, st>>>(ws, splits, Mo, Nin, taps, dw, accumulate, swapped);
   return check_launch("wgrad_reduce");
 }
 
@@ -259,7 +283,7 @@ int simt_wgrad_launch(const void* a, int lda, const void* b, int ldb, float* dw,
   k_wgrad_simt<T><<<grid, 256, 0, st>>>((const T*)a, lda, (const T*)b, ldb, (float*)workspace, g, Mo, Nin, pps);
   int rc = check_launch("wgrad_simt");
   if (rc) return rc;
-  return launch_wgrad_reduce((const float*)workspace, splits, Mo, Nin, taps, dw, accumulate, st);
+  return launch_wgrad_reduce((const float*)workspace, splits, Mo, Nin, taps, dw, accumulate, st, 0);
 }
 
 template int simt_conv_launch<float>(const void*, int, const void*, const float*, void*, int, float*, ConvGeom, float*, int*, cudaStream_t);

@@ -109,6 +109,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// elect.sync: exactly one lane of a converged warp returns true.  The compiler knows the guarded region runs
+// on a single thread, so tcgen05/TMA operands move to uniform registers directly; guarding with
+// `lane == 0` instead makes it wrap EVERY such instruction in an ELECT/BRA.U.ANY waterfall loop (~100
+// cycles per MMA issue -- measured: N=64/128 tiles were issue-bound).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ------------------------------------------------------------------------------------------
@@ -217,7 +233,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n) {
         const int txi = mt % p.tiles_w, tyi = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
@@ -253,23 +269,25 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n, ++it) {
-        const int buf = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
+    // the whole warp walks the pipeline in uniform control flow; one elected lane issues MMAs and commits
+    constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::stage);
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stage * Cfg::stage;
           if constexpr (ROW) {
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {          // three taps out of one box: start += dx pixel rows, base offset = dx
+            for (int dx = 0; dx < 3; ++dx) {          // three taps out of one box: start += dx pixel rows
               const uint64_t adesc = make_sdesc(sa + dx * 128, 16, 1024);   // swizzle is a function of the smem address bits: base offset stays 0 (verified on B200)
               const uint64_t bdesc = make_sdesc(sa + Cfg::stageA + dx * BN * 128, 16, 1024);
 #pragma unroll
@@ -284,9 +302,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
               tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
           tc_commit(&empty_bar[stage]);
-          if (++stage == S) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) tc_commit(&tfull_bar[buf]);
         }
-        tc_commit(&tfull_bar[buf]);
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -310,7 +329,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 #pragma unroll
       for (int c64 = 0; c64 < BN / 64; ++c64, ++chunk_ctr) {
         uint8_t* stg = staging + (chunk_ctr % Cfg::nstaging) * 16384;
-        if (epi_tid == 0) tma_store_wait_read<Cfg::nstaging - 1>();    // the store that last used this buffer has drained
+        if (q == 0 && elect_one()) tma_store_wait_read<Cfg::nstaging - 1>();    // the store that last used this buffer has drained
         named_bar_sync(kEpiBar0, 128);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -341,16 +360,19 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         }
         fence_proxy_async();
         named_bar_sync(kEpiBar1, 128);
-        if (epi_tid == 0) {
-          tma_store_4d(&mapO, stg, n0 + c64 * 64, w0, h0, b);
-          tma_store_commit();
+        if (q == 0) {                 // bulk-group state is per thread: elect.sync picks the same lane for the same mask every time
+          if (elect_one()) {
+            tma_store_4d(&mapO, stg, n0 + c64 * 64, w0, h0, b);
+            tma_store_commit();
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
-    if (epi_tid == 0) tma_store_wait_all();
+    if (q == 0 && elect_one()) tma_store_wait_all();
     if (p.partials) {
       named_bar_sync(kEpiBar0, 128);
       float* red = reinterpret_cast<float*>(staging);   // [4 warps][2][BN]
@@ -429,7 +451,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int dh = 0, dw = 0;
       const CUtensorMap* mB = &mapB0;
       if (p.tap_mode == TAP_CONV3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
@@ -450,13 +472,14 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, 1, 1);
-      int stage = 0; uint32_t phase = 0;
-      for (int pt = pt_begin; pt < pt_end; ++pt) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::stage);
+    constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0; uint32_t phase = 0;
+    for (int pt = pt_begin; pt < pt_end; ++pt) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_base + stage * Cfg::stage;
         // MN-major, 128B swizzle: LBO = stride between 64-channel atoms (8 KB), SBO = 8 pixel rows (1 KB)
         const uint64_t adesc = make_sdesc(sa, 8192, 1024);
         const uint64_t bdesc = make_sdesc(sa + Cfg::stageA, 8192, 1024);
@@ -464,10 +487,12 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         for (int k = 0; k < 4; ++k)       // 64 pixels = 4 x UMMA_K(16): advance 16 rows = 2 KB
           tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (pt > pt_begin) || (k > 0));
         tc_commit(&empty_bar[stage]);
-        if (++stage == S) { stage = 0; phase ^= 1; }
       }
-      tc_commit(tfull_bar);
+      __syncwarp();
+      if (++stage == S) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) tc_commit(tfull_bar);
+    __syncwarp();
   } else if (warp >= 4) {
     const int q = warp - 4;
     const int m = m_tile * 128 + q * 32 + lane;
@@ -489,6 +514,137 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight-gradient kernel, ROW mode (3x3):  D_dx[m][n] = sum_pixels TA[p][m] * TB[p + (dy-1, dx-1)][n]
+// ------------------------------------------------------------------------------------------
+// One CTA = (dy, 128 M-side channels, BN N-side channels, K split).  The K loop walks row segments of TW
+// pixels; per segment ONE box of the unshifted M-side tensor and ONE box of TW+8 pixels of the N-side
+// tensor (starting at w0-1 of row h+dy-1; TMA zero-fills the padding) are loaded, and the three dx taps are
+// three UMMA descriptors into that same box, start address advanced by dx pixel rows (128 B) -- the 128B
+// swizzle is a function of the shared-memory address, so a row-shifted MN-major view stays consistent with
+// what TMA wrote.  Three accumulators (one per dx) live in TMEM for the whole CTA.  Compared with
+// k_tc_wgrad (one tap per CTA) both operands cross L2->SM three times less often.
+struct TcWgradRowParams {
+  int B, H, W;
+  int Mo, Nn;                 // valid channels on the M side / N side
+  int TW, segs_w, nsegs;      // row segments
+  int m_tiles, n_tiles, splits, segs_per_split;
+  int flip;                   // 1: operands swapped (M side = x, N side = dy shifted by -(tap)): tap index 8 - t
+  float* ws;                  // [splits][Mo][9 * Nn]
+};
+template <int BN> struct WgRowCfg {
+  static constexpr uint32_t stageA = 2 * 64 * 128;                 // two 64-channel atoms x <= 64 pixels
+  static constexpr uint32_t atomB = 72 * 128;                      // <= 72 pixel rows per 64-channel atom
+  static constexpr uint32_t stageB = (BN / 64) * atomB;
+  static constexpr uint32_t stage = stageA + stageB;
+  static constexpr int stages = BN == 128 ? 6 : 8;
+  static constexpr uint32_t tmem_cols = BN == 128 ? 512 : 256;
+  static constexpr uint32_t smem = stages * stage + 1024 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+k_tc_wgrad_row(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcWgradRowParams p) {
+  using Cfg = WgRowCfg<BN>;
+  constexpr int S = Cfg::stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + S * Cfg::stage);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint32_t* tmem_holder = (uint32_t*)(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int wi = blockIdx.x;
+  const int dy = wi % 3; wi /= 3;
+  const int n_tile = wi % p.n_tiles; wi /= p.n_tiles;
+  const int m_tile = wi % p.m_tiles; wi /= p.m_tiles;
+  const int split = wi;
+  const int sg_begin = split * p.segs_per_split;
+  const int sg_end = min(sg_begin + p.segs_per_split, p.nsegs);
+  const uint32_t atomA = (uint32_t)p.TW * 128, atomB = (uint32_t)(p.TW + 8) * 128;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, Cfg::tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx = 2 * atomA + (BN / 64) * atomB;
+      for (int sg = sg_begin; sg < sg_end; ++sg) {
+        const int ws_ = sg % p.segs_w, h = (sg / p.segs_w) % p.H, b = sg / (p.segs_w * p.H);
+        const int w0 = ws_ * p.TW;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::stage;
+        mbar_expect_tx(&full_bar[stage], tx);
+        tma_load_4d(sa, &mapA, &full_bar[stage], m_tile * 128, w0, h, b);
+        tma_load_4d(sa + atomA, &mapA, &full_bar[stage], m_tile * 128 + 64, w0, h, b);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(sa + Cfg::stageA + j * atomB, &mapB, &full_bar[stage], n_tile * BN + j * 64, w0 - 1, h + dy - 1, b);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // the whole warp walks the pipeline (uniform control flow); one elected lane issues the MMAs
+    constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+    const int kslices = p.TW >> 4;
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0; uint32_t phase = 0;
+    for (int sg = sg_begin; sg < sg_end; ++sg) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_base + stage * Cfg::stage;
+        const uint64_t adesc = make_sdesc(sa, atomA, 1024);
+        const uint64_t bdesc = make_sdesc(sa + Cfg::stageA, atomB, 1024);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+          for (int k = 0; k < kslices; ++k)        // 16 pixel rows = 2 KB per K slice; dx shifts the N-side view by one row
+            tc_mma_bf16(tmem_base + dx * BN, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(dx * 8 + k * 128), idesc, (sg > sg_begin) || (k > 0));
+        tc_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      if (++stage == S) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) tc_commit(tfull_bar);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int m = m_tile * 128 + q * 32 + lane;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int t = p.flip ? 8 - (dy * 3 + dx) : dy * 3 + dx;
+#pragma unroll
+      for (int c32 = 0; c32 < BN / 32; ++c32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dx * BN + c32 * 32), v);
+        const int c = n_tile * BN + c32 * 32;
+        if (m < p.Mo && c < p.Nn && sg_end > sg_begin) {
+          float* dst = p.ws + (((size_t)split * p.Mo + m) * 9 + t) * p.Nn + c;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -681,7 +837,7 @@ int tc_convT_dgrad(const void* dy, int lddy, const void* wd, void* dx, int lddx,
   return launch_fwd<64>(a, 4, wd, Ktot, o, p, st);
 }
 
-int launch_wgrad_reduce(const float* ws, int splits, int Mo, int Nin, int taps, float* dw, int accumulate, cudaStream_t st);
+int launch_wgrad_reduce(const float* ws, int splits, int Mo, int Nin, int taps, float* dw, int accumulate, cudaStream_t st, int swapped);
 
 struct WgPlan { int TW, TH, tiles_w, tiles_h, pix_tiles, m_tiles, n_tiles, BN, splits, tps; };
 static WgPlan plan_wgrad(int B, int H, int W, int Mo, int Nin, int ntaps) {
@@ -741,7 +897,68 @@ static int tc_wgrad_generic(const ActView& a, const ActView* bviews, int nb, int
   p.ws = (float*)workspace;
   int rc = g.BN == 256 ? launch_wgrad<256>(a, bviews, nb, p, st) : (g.BN == 128 ? launch_wgrad<128>(a, bviews, nb, p, st) : launch_wgrad<64>(a, bviews, nb, p, st));
   if (rc) return rc;
-  return launch_wgrad_reduce((const float*)workspace, g.splits, Mo, Nin, ntaps, dw, accumulate, st);
+  return launch_wgrad_reduce((const float*)workspace, g.splits, Mo, Nin, ntaps, dw, accumulate, st, 0);
+}
+
+// ---- row-mode plan (3x3) --------------------------------------------------------------------
+static int wgrad_row_mode() {      // USTRUN_TC_WGRAD_ROW=0 falls back to the one-tap-per-CTA kernel (A/B comparisons)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USTRUN_TC_WGRAD_ROW");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+struct WgRowPlan { bool ok; int swap, Mo, Nn, BN, TW, segs_w, nsegs, m_tiles, n_tiles, splits, sps; };
+static WgRowPlan plan_wgrad_row(int B, int H, int W, int Cin, int Cout, int ksize) {
+  WgRowPlan g{};
+  g.ok = false;
+  if (ksize != 3 || wgrad_row_mode() <= 0) return g;
+  int TW = 0;
+  for (int tw : {64, 48, 32})
+    if (W % tw == 0) { TW = tw; break; }
+  if (!TW && W < 64 && W >= 16) TW = (W + 15) / 16 * 16;           // one zero-padded segment per row
+  if (!TW) return g;
+  g.TW = TW;
+  g.segs_w = (W + TW - 1) / TW;
+  g.nsegs = B * H * g.segs_w;
+  // M side = the unshifted tensor.  Default: dy (Cout rows).  With Cout == 64 < Cin the operands swap so that
+  // no half of the 128-row MMA is idle: M side = x (Cin rows), N side = dy shifted by -(tap).
+  g.swap = (Cout == 64 && Cin >= 128) ? 1 : 0;
+  g.Mo = g.swap ? Cin : Cout;
+  g.Nn = g.swap ? Cout : Cin;
+  g.BN = g.Nn % 128 == 0 ? 128 : 64;
+  g.m_tiles = (g.Mo + 127) / 128;
+  g.n_tiles = g.Nn / g.BN;
+  const long long items = 3LL * g.m_tiles * g.n_tiles;
+  long long want = num_sms() / items;                                // one wave of CTAs (1 CTA / SM)
+  if (want < 1) want = 1;
+  long long maxs = (g.nsegs + 15) / 16;                              // >= 16 segments per split
+  if (maxs < 1) maxs = 1;
+  if (want > maxs) want = maxs;
+  g.sps = (int)((g.nsegs + want - 1) / want);
+  g.splits = (g.nsegs + g.sps - 1) / g.sps;
+  g.ok = true;
+  return g;
+}
+
+template <int BN>
+static int launch_wgrad_row(const ActView& a, const ActView& b, const WgRowPlan& g, TcWgradRowParams p, cudaStream_t st) {
+  using Cfg = WgRowCfg<BN>;
+  CUtensorMap mA, mB;
+  int rc = make_act_map(&mA, a.base, a.C, a.W, a.H, a.B, a.sw, a.sh, a.sb, g.TW, 1);
+  if (rc) return rc;
+  rc = make_act_map(&mB, b.base, b.C, b.W, b.H, b.B, b.sw, b.sh, b.sb, g.TW + 8, 1);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad_row<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_tc_wgrad_row<%d>): %s", BN, cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  const int grid = 3 * g.m_tiles * g.n_tiles * g.splits;
+  k_tc_wgrad_row<BN><<<grid, 256, Cfg::smem, st>>>(mA, mB, p);
+  return check_launch("k_tc_wgrad_row");
 }
 
 int tc_conv_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout, int ksize,
@@ -749,9 +966,27 @@ int tc_conv_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, i
   if (Cin % 64 || Cout % 64 || lddy % 8 || ldx % 8) { set_error("tcgen05 wgrad needs Cin, Cout %% 64 == 0"); return USTRUN_ERR_ARG; }
   ActView a{dy, Cout, W, H, B, lddy, (long long)W * lddy, (long long)H * W * lddy};
   ActView b{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
+  WgRowPlan g = plan_wgrad_row(B, H, W, Cin, Cout, ksize);
+  if (g.ok) {
+    long long need = (long long)g.splits * Cout * 9 * Cin * (long long)sizeof(float);
+    if (!workspace || ws_bytes < need) { set_error("tc wgrad (row): workspace too small (%lld < %lld)", ws_bytes, need); return USTRUN_ERR_ARG; }
+    TcWgradRowParams p{};
+    p.B = B; p.H = H; p.W = W; p.Mo = g.Mo; p.Nn = g.Nn; p.TW = g.TW; p.segs_w = g.segs_w; p.nsegs = g.nsegs;
+    p.m_tiles = g.m_tiles; p.n_tiles = g.n_tiles; p.splits = g.splits; p.segs_per_split = g.sps; p.flip = g.swap;
+    p.ws = (float*)workspace;
+    const ActView& ma = g.swap ? b : a;
+    const ActView& nb = g.swap ? a : b;
+    int rc = g.BN == 128 ? launch_wgrad_row<128>(ma, nb, g, p, st) : launch_wgrad_row<64>(ma, nb, g, p, st);
+    if (rc) return rc;
+    return launch_wgrad_reduce((const float*)workspace, g.splits, g.Mo, g.Nn, 9, dw, accumulate, st, g.swap);
+  }
   return tc_wgrad_generic(a, &b, 1, ksize == 3 ? TAP_CONV3 : TAP_NONE, ksize * ksize, B, H, W, Cout, Cin, dw, accumulate, workspace, ws_bytes, st);
 }
-long long tc_conv_wgrad_ws(int B, int H, int W, int Cin, int Cout, int ksize) { return tc_wgrad_ws_bytes(B, H, W, Cout, Cin, ksize * ksize); }
+long long tc_conv_wgrad_ws(int B, int H, int W, int Cin, int Cout, int ksize) {
+  WgRowPlan g = plan_wgrad_row(B, H, W, Cin, Cout, ksize);
+  if (g.ok) return (long long)g.splits * Cout * 9 * Cin * (long long)sizeof(float);
+  return tc_wgrad_ws_bytes(B, H, W, Cout, Cin, ksize * ksize);
+}
 
 // dW[ci][co][ij] = sum_p x[p][ci] * dy[b,2h+i,2w+j][co]
 int tc_convT_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout,
