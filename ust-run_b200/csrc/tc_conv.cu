@@ -146,10 +146,14 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
   return d;
 }
 
-// lane j of the warp returns sum over the 32 lanes of v[j]  (31 shuffles for 32 columns)
-__device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
+// Column sums over the 32 lanes of a warp by a halving butterfly: level o (16, 8, .., 1) leaves o values per lane.
+// butterfly_levels<HI, LO> runs levels HI, HI/2, .., LO on v[0 .. 2*HI); after level 1 lane j holds the total of
+// column j.  All levels are linear, so the first levels can run per tile and the rest once per CTA on
+// accumulated partials (see the epilogue: 128 accumulator registers for every BN).
+template <int HI, int LO>
+__device__ __forceinline__ void butterfly_levels(float* v, int lane) {
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
+  for (int o = HI; o >= LO; o >>= 1) {
     const bool hi = (lane & o) != 0;
 #pragma unroll
     for (int i = 0; i < o; ++i) {
@@ -158,7 +162,6 @@ __device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
     }
   }
-  return v[0];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -174,6 +177,8 @@ struct TcConvParams {
   int m_tiles, n_tiles, ctas_per_n;
   float* partials;       // [ctas_per_n][2][Cout] or null
   const float* bias;     // [Cout] or null
+  int stages, nstaging;  // RESB only: depth of the activation ring / number of 16 KB store staging buffers
+  uint32_t wres_bytes;   // RESB only: bytes of the resident weight block (ntaps * Cin/64 slots of BN x 128 B)
 };
 
 constexpr int kEpiBar0 = 1, kEpiBar1 = 2;
@@ -195,21 +200,30 @@ template <int BN, bool ROW> struct FwdCfg {
   static constexpr uint32_t smem = stages * stage + nstaging * 16384 + 1024 /*barriers*/ + 1024 /*align slack*/;
 };
 
-template <int BN, bool ROW>
+// RESB ("resident B"): when the whole weight block of the CTA's N tile fits in shared memory (<= ~147 KB: the
+// 64/128-channel layers at the top of the UNet) it is loaded ONCE per CTA and the ring carries activations
+// only.  Those layers were bound by re-loading the weights for every 128-pixel tile (L2->SM traffic and
+// shared-memory fill bandwidth), not by the tensor pipe.
+template <int BN, bool ROW, bool RESB>
 __global__ void __launch_bounds__(256, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
           const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
           const TcConvParams p) {
   using Cfg = FwdCfg<BN, ROW>;
-  constexpr int S = Cfg::stages;
+  const int S = RESB ? p.stages : Cfg::stages;
+  const int nstg = RESB ? p.nstaging : Cfg::nstaging;
+  const uint32_t stage_stride = RESB ? Cfg::stageA : Cfg::stage;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + S * Cfg::stage;
-  uint64_t* full_bar = (uint64_t*)(staging + Cfg::nstaging * 16384);
-  uint64_t* empty_bar = full_bar + S;
-  uint64_t* tfull_bar = empty_bar + S;
+  uint8_t* smem_al = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wres = smem_al;                                       // RESB: [ntaps * kchunks][BN rows x 128 B]
+  uint8_t* smem = smem_al + (RESB ? p.wres_bytes : 0u);          // the ring
+  uint8_t* staging = smem + S * stage_stride;
+  uint64_t* full_bar = (uint64_t*)(staging + nstg * 16384);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_holder = (uint32_t*)(tempty_bar + 2);
+  uint64_t* wres_bar = tempty_bar + 2;
+  uint32_t* tmem_holder = (uint32_t*)(wres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x % p.n_tiles;
@@ -224,6 +238,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     prefetch_tmap(&mapO);
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    mbar_init(wres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_holder, 2 * BN);
@@ -234,6 +249,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (elect_one()) {
+      if constexpr (RESB) {                    // the CTA's whole weight block, once
+        mbar_expect_tx(wres_bar, p.wres_bytes);
+        const int nslots = p.ntaps * kchunks;
+        for (int i = 0; i < nslots; ++i) tma_load_2d(wres + (size_t)i * BN * 128, &mapW, wres_bar, i * 64, n0);
+      }
       int stage = 0; uint32_t phase = 0;
       for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n) {
         const int txi = mt % p.tiles_w, tyi = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
@@ -242,12 +262,14 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           for (int dy = 0; dy < 3; ++dy)
             for (int kc = 0; kc < kchunks; ++kc) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * Cfg::stage;
-              mbar_expect_tx(&full_bar[stage], Cfg::stage);
+              uint8_t* sa = smem + stage * stage_stride;
+              mbar_expect_tx(&full_bar[stage], stage_stride);
               tma_load_4d(sa, &mapA1, &full_bar[stage], kc * 64, w0 - 1, h0 + dy - 1, b);      // mapA1: box of 136 pixels
+              if constexpr (!RESB) {
 #pragma unroll
-              for (int dx = 0; dx < 3; ++dx)
-                tma_load_2d(sa + Cfg::stageA + dx * BN * 128, &mapW, &full_bar[stage], ((dy * 3 + dx) * kchunks + kc) * 64, n0);
+                for (int dx = 0; dx < 3; ++dx)
+                  tma_load_2d(sa + Cfg::stageA + dx * BN * 128, &mapW, &full_bar[stage], ((dy * 3 + dx) * kchunks + kc) * 64, n0);
+              }
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
           continue;
@@ -259,62 +281,83 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           else if (p.tap_mode == TAP_PERMAP) mA = tap == 0 ? &mapA0 : (tap == 1 ? &mapA1 : (tap == 2 ? &mapA2 : &mapA3));
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::stage;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)(p.TH * p.TW * 128) + Cfg::stageB);
+            uint8_t* sa = smem + stage * stage_stride;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)(p.TH * p.TW * 128) + (RESB ? 0u : Cfg::stageB));
             tma_load_4d(sa, mA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, b);
-            tma_load_2d(sa + Cfg::stageA, &mapW, &full_bar[stage], (tap * kchunks + kc) * 64, n0);
+            if constexpr (!RESB) tma_load_2d(sa + Cfg::stageA, &mapW, &full_bar[stage], (tap * kchunks + kc) * 64, n0);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // the whole warp walks the pipeline in uniform control flow; one elected lane issues MMAs and commits
-    constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-    const uint32_t smem_base = smem_u32(smem);
-    int stage = 0; uint32_t phase = 0;
-    int it = 0;
-    for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n, ++it) {
-      const int buf = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // One elected lane walks the pipeline and issues every MMA.  The per-stage work of this thread is the
+    // critical path of the narrow tiles (a stage is only 4..12 MMAs of 48..128 cycles), so the 64-bit
+    // shared-memory descriptors are never rebuilt: `a_cur` / `b_cur` advance by the stage stride (the 14-bit
+    // address field cannot carry: addresses < 256 KB) and every MMA adds a compile-time constant.
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+      const uint64_t a_first = make_sdesc(smem_u32(smem), 16, 1024);
+      const uint64_t stride_d = (uint64_t)(stage_stride >> 4);
+      const uint64_t w_first = make_sdesc(smem_u32(wres), 16, 1024);       // RESB: slot 0 of the resident weights
+      constexpr uint64_t kSlotD = (uint64_t)(BN * 128) >> 4;               // one weight slot (BN rows x 128 B)
+      constexpr uint64_t kBoffD = (uint64_t)Cfg::stageA >> 4;              // non-RESB: weights sit behind the A box of the stage
+      uint64_t a_cur = a_first;
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      if constexpr (RESB) { mbar_wait(wres_bar, 0); tc_fence_after(); }
+      for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_base + stage * Cfg::stage;
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        uint64_t w_cur = w_first;                                          // RESB: walks the slots in producer order
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
           if constexpr (ROW) {
+            // stage = (dy, channel chunk); slots of its three dx taps: ((dy*3 + dx) * kchunks + kc)
+            const uint64_t b0 = RESB ? w_cur : a_cur + kBoffD;
+            const uint64_t bdx = RESB ? (uint64_t)kchunks * kSlotD : kSlotD;
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {          // three taps out of one box: start += dx pixel rows
-              const uint64_t adesc = make_sdesc(sa + dx * 128, 16, 1024);   // swizzle is a function of the smem address bits: base offset stays 0 (verified on B200)
-              const uint64_t bdesc = make_sdesc(sa + Cfg::stageA + dx * BN * 128, 16, 1024);
+            for (int dx = 0; dx < 3; ++dx) {          // three taps out of one box: start += dx pixel rows (128 B = 8 descriptor units)
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | dx | k) != 0);
+                tc_mma_bf16(d_tmem, a_cur + (uint64_t)(dx * 8 + k * 2), b0 + (uint64_t)dx * bdx + (uint64_t)(k * 2), idesc, (kb | dx | k) != 0);
+            }
+            if constexpr (RESB) {                     // next stage: kc+1, or (dy+1, kc=0) = +2*kchunks slots further
+              if ((kb + 1) % kchunks == 0) w_cur += (uint64_t)(2 * kchunks + 1) * kSlotD;
+              else w_cur += kSlotD;
             }
           } else {
-            const uint64_t adesc = make_sdesc(sa, 16, 1024);
-            const uint64_t bdesc = make_sdesc(sa + Cfg::stageA, 16, 1024);
+            const uint64_t b0 = RESB ? w_cur : a_cur + kBoffD;
 #pragma unroll
             for (int k = 0; k < 4; ++k)     // 64 channels = 4 x UMMA_K(16); +32 B inside the swizzle row
-              tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              tc_mma_bf16(d_tmem, a_cur + (uint64_t)(k * 2), b0 + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if constexpr (RESB) w_cur += kSlotD;
           }
           tc_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) tc_commit(&tfull_bar[buf]);
+          a_cur += stride_d;
+          if (++stage == S) { stage = 0; phase ^= 1; a_cur = a_first; }
         }
-        __syncwarp();
-        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     const int q = warp - 4;                     // TMEM lane quadrant
     const int row = q * 32 + lane;              // pixel row inside the tile
     const int epi_tid = threadIdx.x - 128;
-    float ssum[BN / 32], ssq[BN / 32];
+    // BatchNorm statistics: LV butterfly levels per tile, the remaining levels once per CTA.  Per lane
+    // 2 * (BN/32) * (32 >> LV) = 128 running sums for BN = 64 / 128 / 256 (LV = 0 / 1 / 2).
+    constexpr int LV = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
+    constexpr int NP = 32 >> LV;
+    float asum[BN / 32][NP], asq[BN / 32][NP];
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+    for (int i = 0; i < BN / 32; ++i)
+#pragma unroll
+      for (int j = 0; j < NP; ++j) { asum[i][j] = 0.f; asq[i][j] = 0.f; }
     int it = 0;
     uint32_t chunk_ctr = 0;
     for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n, ++it) {
@@ -324,12 +367,16 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       const int w0 = txi * p.TW, h0 = tyi * p.TH;
       const int th = row / p.TW, tw = row - th * p.TW;
       const bool valid = (row < p.TH * p.TW) && (h0 + th < p.H) && (w0 + tw < p.W);
+      const bool tile_partial = (p.TH * p.TW < 128) || (h0 + p.TH > p.H) || (w0 + p.TW > p.W);
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
 #pragma unroll
       for (int c64 = 0; c64 < BN / 64; ++c64, ++chunk_ctr) {
-        uint8_t* stg = staging + (chunk_ctr % Cfg::nstaging) * 16384;
-        if (q == 0 && elect_one()) tma_store_wait_read<Cfg::nstaging - 1>();    // the store that last used this buffer has drained
+        uint8_t* stg = staging + (chunk_ctr % nstg) * 16384;
+        if (q == 0 && elect_one()) {                                           // the store that last used this buffer has drained
+          if (nstg == 2) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
         named_bar_sync(kEpiBar0, 128);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -351,11 +398,19 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             *reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4)) = val;
           }
           if (p.partials) {
+            if (tile_partial) {                       // warp-uniform: only edge tiles pay for the row mask
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] : 0.f;
+            }
             float sq[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
-            ssum[c32] += butterfly_colsum(v, lane);
-            ssq[c32] += butterfly_colsum(sq, lane);
+            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+            if constexpr (LV > 0) {
+              butterfly_levels<16, (16 >> (LV - 1))>(v, lane);
+              butterfly_levels<16, (16 >> (LV - 1))>(sq, lane);
+            }
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { asum[c32][j] += v[j]; asq[c32][j] += sq[j]; }
           }
         }
         fence_proxy_async();
@@ -378,8 +433,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       float* red = reinterpret_cast<float*>(staging);   // [4 warps][2][BN]
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) {
-        red[(q * 2 + 0) * BN + i * 32 + lane] = ssum[i];
-        red[(q * 2 + 1) * BN + i * 32 + lane] = ssq[i];
+        butterfly_levels<(16 >> LV), 1>(asum[i], lane);        // remaining levels: lane j ends with the total of column j
+        butterfly_levels<(16 >> LV), 1>(asq[i], lane);
+        red[(q * 2 + 0) * BN + i * 32 + lane] = asum[i][0];
+        red[(q * 2 + 1) * BN + i * 32 + lane] = asq[i][0];
       }
       named_bar_sync(kEpiBar1, 128);
       for (int o = epi_tid; o < 2 * BN; o += 128) {
@@ -472,26 +529,25 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(BN, 1, 1);
-    const uint32_t smem_base = smem_u32(smem);
-    int stage = 0; uint32_t phase = 0;
-    for (int pt = pt_begin; pt < pt_end; ++pt) {
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_base + stage * Cfg::stage;
-        // MN-major, 128B swizzle: LBO = stride between 64-channel atoms (8 KB), SBO = 8 pixel rows (1 KB)
-        const uint64_t adesc = make_sdesc(sa, 8192, 1024);
-        const uint64_t bdesc = make_sdesc(sa + Cfg::stageA, 8192, 1024);
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+      // MN-major, 128B swizzle: LBO = stride between 64-channel atoms (8 KB), SBO = 8 pixel rows (1 KB)
+      const uint64_t a_first = make_sdesc(smem_u32(smem), 8192, 1024);
+      constexpr uint64_t kStrideD = (uint64_t)Cfg::stage >> 4, kBoffD = (uint64_t)Cfg::stageA >> 4;
+      uint64_t a_cur = a_first;
+      int stage = 0; uint32_t phase = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)       // 64 pixels = 4 x UMMA_K(16): advance 16 rows = 2 KB
-          tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (pt > pt_begin) || (k > 0));
+          tc_mma_bf16(tmem_base, a_cur + (uint64_t)(k * 128), a_cur + kBoffD + (uint64_t)(k * 128), idesc, (pt > pt_begin) || (k > 0));
         tc_commit(&empty_bar[stage]);
+        a_cur += kStrideD;
+        if (++stage == S) { stage = 0; phase ^= 1; a_cur = a_first; }
       }
-      __syncwarp();
-      if (++stage == S) { stage = 0; phase ^= 1; }
+      tc_commit(tfull_bar);
     }
-    if (elect_one()) tc_commit(tfull_bar);
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp - 4;
@@ -598,28 +654,36 @@ k_tc_wgrad_row(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // the whole warp walks the pipeline (uniform control flow); one elected lane issues the MMAs
-    constexpr uint32_t idesc = make_idesc(BN, 1, 1);
-    const int kslices = p.TW >> 4;
-    const uint32_t smem_base = smem_u32(smem);
-    int stage = 0; uint32_t phase = 0;
-    for (int sg = sg_begin; sg < sg_end; ++sg) {
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_base + stage * Cfg::stage;
-        const uint64_t adesc = make_sdesc(sa, atomA, 1024);
-        const uint64_t bdesc = make_sdesc(sa + Cfg::stageA, atomB, 1024);
+    if (elect_one()) {                  // one thread owns the whole MMA stream; descriptors advance incrementally
+      constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+      constexpr uint32_t idesc3 = make_idesc(192, 1, 1);
+      const int kslices = p.TW >> 4;
+      const uint64_t a_first = make_sdesc(smem_u32(smem), atomA, 1024);
+      // BN == 64: ONE N=192 MMA covers the three dx taps: the N-side "atoms" are the same 64-channel box at a stride
+      // (LBO) of one pixel row, i.e. atom j IS the view shifted by j pixels.  The M-side operand is then read from
+      // shared memory once instead of three times (an N=64 MMA is bound by that read: 48 cycles instead of 32).
+      const uint64_t b_first = make_sdesc(smem_u32(smem) + Cfg::stageA, BN == 64 ? 128u : atomB, 1024);
+      constexpr uint64_t kStrideD = (uint64_t)Cfg::stage >> 4;
+      uint64_t a_cur = a_first, b_cur = b_first;
+      int stage = 0; uint32_t phase = 0;
+      for (int sg = sg_begin; sg < sg_end; ++sg) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if constexpr (BN == 64) {
+          for (int k = 0; k < kslices; ++k)          // 16 pixel rows = 2 KB per K slice
+            tc_mma_bf16(tmem_base, a_cur + (uint64_t)(k * 128), b_cur + (uint64_t)(k * 128), idesc3, (sg > sg_begin) || (k > 0));
+        } else {
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
-          for (int k = 0; k < kslices; ++k)        // 16 pixel rows = 2 KB per K slice; dx shifts the N-side view by one row
-            tc_mma_bf16(tmem_base + dx * BN, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(dx * 8 + k * 128), idesc, (sg > sg_begin) || (k > 0));
+          for (int dx = 0; dx < 3; ++dx)
+            for (int k = 0; k < kslices; ++k)        // dx shifts the N-side view by one pixel row (128 B)
+              tc_mma_bf16(tmem_base + dx * BN, a_cur + (uint64_t)(k * 128), b_cur + (uint64_t)(dx * 8 + k * 128), idesc, (sg > sg_begin) || (k > 0));
+        }
         tc_commit(&empty_bar[stage]);
+        a_cur += kStrideD; b_cur += kStrideD;
+        if (++stage == S) { stage = 0; phase ^= 1; a_cur = a_first; b_cur = b_first; }
       }
-      __syncwarp();
-      if (++stage == S) { stage = 0; phase ^= 1; }
+      tc_commit(tfull_bar);
     }
-    if (elect_one()) tc_commit(tfull_bar);
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp - 4;
@@ -731,9 +795,19 @@ struct ActView {            // NHWC bf16 view in elements
   long long sw, sh, sb;
 };
 
-template <int BN, bool ROW = false>
-static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot, const ActView& out, TcConvParams p, cudaStream_t st) {
-  using Cfg = FwdCfg<BN, ROW>;
+static int resb_mode() {      // USTRUN_TC_RESB=0 disables the resident-weights variant (A/B comparisons)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USTRUN_TC_RESB");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+constexpr uint32_t kMaxDynSmem = 232448;       // 227 KB opt-in limit per CTA on sm_100
+
+template <int BN, bool ROW, bool RESB>
+static int launch_fwd_impl(const ActView* a, int nmaps, const void* w, long long Ktot, const ActView& out, TcConvParams p, uint32_t smem_bytes,
+                           cudaStream_t st) {
   CUtensorMap mA[4], mW, mO;
   for (int i = 0; i < 4; ++i) {
     const ActView& v = a[i < nmaps ? i : 0];
@@ -746,18 +820,45 @@ static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<BN, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_tc_conv<%d,%d>, %u): %s", BN, (int)ROW, Cfg::smem, cudaGetErrorString(e)); return (int)e; }
+    const uint32_t want = RESB ? kMaxDynSmem : smem_bytes;
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<BN, ROW, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_tc_conv<%d,%d,%d>, %u): %s", BN, (int)ROW, (int)RESB, want, cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
+  k_tc_conv<BN, ROW, RESB><<<p.n_tiles * p.ctas_per_n, 256, smem_bytes, st>>>(mA[0], mA[1], mA[2], mA[3], mW, mO, p);
+  return check_launch("k_tc_conv");
+}
+
+template <int BN, bool ROW = false>
+static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot, const ActView& out, TcConvParams p, cudaStream_t st) {
+  using Cfg = FwdCfg<BN, ROW>;
   p.n_tiles = p.Cout / BN;
   int per = num_sms() / p.n_tiles;
   if (per < 1) per = 1;
   if (per > p.m_tiles) per = p.m_tiles;
   if (per > USTRUN_MAX_PARTS) per = USTRUN_MAX_PARTS;
   p.ctas_per_n = per;
-  k_tc_conv<BN, ROW><<<p.n_tiles * per, 256, Cfg::smem, st>>>(mA[0], mA[1], mA[2], mA[3], mW, mO, p);
-  return check_launch("k_tc_conv");
+  if constexpr (BN <= 128) {
+    // resident weights: the N tile's whole [BN][Ktot] block stays in shared memory, the ring carries activations only
+    const long long wres = Ktot * BN * 2;
+    const int tiles_per_cta = (p.m_tiles + per - 1) / per;
+    // measured on B200 (profiles/r01_kernel_microbench_cfg2.txt): pays off for the row-mode N=128 tiles (3 x 16 KB of
+    // weights per stage otherwise); for N=64 tiles the weight slots are small and the plain ring is as fast
+    if ((resb_mode() > 1 || (resb_mode() == 1 && ROW && BN == 128)) && wres <= 148 * 1024 && tiles_per_cta >= 3) {
+      const long long avail = (long long)kMaxDynSmem - 2048 - wres;
+      int nstg = 2;
+      long long stages = (avail - nstg * 16384) / Cfg::stageA;
+      if (stages < 4) { nstg = 1; stages = (avail - nstg * 16384) / Cfg::stageA; }
+      if (stages > 8) stages = 8;
+      { static int cap = -1; if (cap < 0) { const char* e = getenv("USTRUN_TC_RESB_STAGES"); cap = e ? atoi(e) : 8; } if (stages > cap) stages = cap; }
+      if (stages >= 3) {
+        p.stages = (int)stages; p.nstaging = nstg; p.wres_bytes = (uint32_t)wres;
+        const uint32_t smem_bytes = (uint32_t)(wres + stages * Cfg::stageA + nstg * 16384 + 2048);
+        return launch_fwd_impl<BN, ROW, true>(a, nmaps, w, Ktot, out, p, smem_bytes, st);
+      }
+    }
+  }
+  return launch_fwd_impl<BN, ROW, false>(a, nmaps, w, Ktot, out, p, Cfg::smem, st);
 }
 
 // x: [B,H,W,Cin] (ldx), y: [B,H,W,Cout] (ldy); generic entry used by conv3x3/1x1 fwd+dgrad
