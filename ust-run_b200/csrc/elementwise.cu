@@ -234,24 +234,25 @@ __global__ void k_bn_act_pool(const T* __restrict__ x, int ldx, const float* __r
   }
 }
 
-// partial sums of (g', g'*xhat) per channel. 256 threads; thread owns channel group tid % CG.
+// partial sums of (g', g'*xhat) per channel, g' = g * act'(bn(x)).  256 threads; a thread owns channel group
+// tid % CG.  The loop accumulates sum g' and sum g'*x only (2 FMAs per element); xhat = (x - mean) * rstd is
+// applied to the block totals: sum g'*xhat = rstd * (sum g'*x - mean * sum g').
 template <typename T>
-__global__ void k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ldx,
-                                const float* __restrict__ mean, const float* __restrict__ rstd,
-                                const float* __restrict__ scale, const float* __restrict__ shift, int act, long long npix,
-                                int C, float* __restrict__ partials) {
-  extern __shared__ float sm[];   // [256][16]
-  int CG = C >> 3;
-  int tid = threadIdx.x;
+__global__ void __launch_bounds__(256, 3)
+k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ldx,
+                const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ scale, const float* __restrict__ shift, int act, long long npix,
+                int C, float* __restrict__ partials) {
+  extern __shared__ float sm[];   // [16][256]
+  const int CG = C >> 3;
+  const int tid = threadIdx.x;
   float acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-  if (CG <= 256) {
-    int cg = tid % CG;
-    int lanes = 256 / CG;                       // pixel lanes per block
-    float mu[8], rs[8], sc[8], sh[8];
-    Vec8<float>::load(mean + cg * 8, mu);
-    Vec8<float>::load(rstd + cg * 8, rs);
+  {
+    const int cg = tid % CG;
+    const int lanes = 256 / CG;                       // pixel lanes per block
+    float sc[8], sh[8];
     Vec8<float>::load(scale + cg * 8, sc);
     Vec8<float>::load(shift + cg * 8, sh);
 #pragma unroll 4
@@ -261,22 +262,25 @@ __global__ void k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __res
       Vec8<T>::load(x + p * ldx + cg * 8, xv);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float gp = gv[k] * act_grad(fmaf(xv[k], sc[k], sh[k]), act);
+        const float gp = gv[k] * act_grad(fmaf(xv[k], sc[k], sh[k]), act);
         acc[k] += gp;
-        acc[8 + k] += gp * ((xv[k] - mu[k]) * rs[k]);
+        acc[8 + k] = fmaf(gp, xv[k], acc[8 + k]);
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < 16; ++k) sm[tid * 16 + k] = acc[k];
+  for (int k = 0; k < 16; ++k) sm[k * 256 + tid] = acc[k];
   __syncthreads();
-  int lanes = 256 / CG;
-  for (int o = tid; o < 2 * C; o += 256) {
-    int which = o / C, c = o % C;
-    int cg = c >> 3, k = (c & 7) + which * 8;
-    float s = 0.f;
-    for (int l = 0; l < lanes; ++l) s += sm[(l * CG + cg) * 16 + k];
-    partials[(size_t)blockIdx.x * 2 * C + o] = s;
+  const int lanes = 256 / CG;
+  for (int c = tid; c < C; c += 256) {
+    const int cg = c >> 3, k = c & 7;
+    float s1 = 0.f, s2 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      s1 += sm[k * 256 + l * CG + cg];
+      s2 += sm[(8 + k) * 256 + l * CG + cg];
+    }
+    partials[(size_t)blockIdx.x * 2 * C + c] = s1;
+    partials[(size_t)blockIdx.x * 2 * C + C + c] = rstd[c] * (s2 - mean[c] * s1);
   }
 }
 
@@ -609,9 +613,9 @@ int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const f
   USTRUN_REQUIRE(g && x && mean && rstd && scale && shift && partials && nparts_host, "bn_bwd_reduce: null arg");
   USTRUN_REQUIRE(C % 8 == 0 && ldg % 8 == 0 && ldx % 8 == 0 && (C / 8) <= 256 && 256 % (C / 8) == 0, "bn_bwd_reduce: C=%d unsupported", C);
   int lanes = 256 / (C / 8);
-  int grid = (int)((npix + lanes - 1) / lanes);
-  if (grid > USTRUN_MAX_PARTS) grid = USTRUN_MAX_PARTS;
-  if (grid > 148 * 8) grid = 148 * 8;
+  int grid = (int)((npix + 4LL * lanes - 1) / (4LL * lanes));       // >= 4 pixels per thread
+  if (grid < 1) grid = 1;
+  if (grid > 148 * 6) grid = 148 * 6;                                // two waves of 3 resident blocks per SM
   *nparts_host = grid;
   DISPATCH_DTYPE(dtype, (k_bn_bwd_reduce<T><<<grid, 256, 256 * 16 * sizeof(float), (cudaStream_t)stream>>>(
                             (const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale, shift, act, npix, C, partials)));

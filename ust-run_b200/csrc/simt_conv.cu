@@ -193,49 +193,44 @@ k_wgrad_simt(const T* __restrict__ a, int lda, const T* __restrict__ bsrc, int l
   }
 }
 
-// dw[(m*Nin + c)*taps + t] (+)= sum_s ws[s][m][t*Nin + c].  A block owns (m, 32 consecutive c): the split
-// partials are read as 128-byte runs along c for every tap, summed, transposed through shared memory and
-// written (read-modify-write when accumulating) as one contiguous run of 32*taps floats of the OIHW tensor.
-__global__ void __launch_bounds__(128)
-k_wgrad_reduce(const float* __restrict__ ws, int splits, int Mo, int Nin, int taps, float* __restrict__ dw, int accumulate, int swapped) {
-  __shared__ float tile[9][33];
-  const int cchunks = (Nin + 31) >> 5;
-  const long long n = (long long)Mo * Nin * taps;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  for (long long item = blockIdx.x; item < (long long)Mo * cchunks; item += gridDim.x) {
-    const int m = (int)(item / cchunks), c0 = (int)(item - (long long)m * cchunks) * 32;
-    const int nc = min(32, Nin - c0);
-    for (int t = wrp; t < taps; t += 4) {
-      float s = 0.f;
-      if (lane < nc) {
-        const float* src = ws + ((size_t)m * taps + t) * Nin + c0 + lane;
-        for (int k = 0; k < splits; ++k) s += src[(size_t)k * n];
-      }
-      tile[t][lane] = s;
+// dw[(m*Nin + c)*taps + t] (+)= sum_s ws[s][m][t*Nin + c].  One thread per (m, c): its taps*splits loads are all
+// independent (coalesced across the warp along c), and its `taps` results are one contiguous run of the OIHW tensor,
+// so a warp reads/writes 32*taps consecutive floats.  No shared memory, no barriers: the kernel is pure memory-level
+// parallelism (the previous block-per-tile version was latency-bound at ~36 us per call).
+template <int TAPS>
+__global__ void __launch_bounds__(256)
+k_wgrad_reduce(const float* __restrict__ ws, int splits, int Mo, int Nin, float* __restrict__ dw, int accumulate, int swapped) {
+  const long long n = (long long)Mo * Nin * TAPS, pairs = (long long)Mo * Nin;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < pairs; j += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(j / Nin), c = (int)(j - (long long)m * Nin);
+    float acc[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) acc[t] = 0.f;
+    const float* src = ws + ((size_t)m * TAPS) * Nin + c;
+    for (int k = 0; k < splits; ++k) {
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) acc[t] += src[(size_t)k * n + (size_t)t * Nin];
     }
-    __syncthreads();
-    if (!swapped) {
-      float* dst = dw + ((size_t)m * Nin + c0) * taps;
-      for (int i = threadIdx.x; i < nc * taps; i += 128) {
-        const int c = i / taps, t = i - c * taps;
-        dst[i] = (accumulate ? dst[i] : 0.f) + tile[t][c];
-      }
-    } else {                                       // ws rows are input channels: dw[(c*Mo + m)*taps + t]
-      for (int i = threadIdx.x; i < nc * taps; i += 128) {
-        const int c = i / taps, t = i - c * taps;
-        float* d = dw + ((size_t)(c0 + c) * Mo + m) * taps + t;
-        *d = (accumulate ? *d : 0.f) + tile[t][c];
-      }
+    float* dst = swapped ? dw + ((size_t)c * Mo + m) * TAPS : dw + (size_t)j * TAPS;   // swapped: ws rows are input channels
+    if (accumulate) {
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) acc[t] += dst[t];
     }
-    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) dst[t] = acc[t];
   }
 }
 
 int launch_wgrad_reduce(const float* ws, int splits, int Mo, int Nin, int taps, float* dw, int accumulate, cudaStream_t st, int swapped) {
-  if (taps > 9) { set_error("wgrad_reduce: taps > 9"); return USTRUN_ERR_ARG; }
-  long long items = (long long)Mo * ((Nin + 31) / 32);
-  int rb = (int)(items < 148 * 16 ? items : 148 * 16);
-  k_wgrad_reduce<<<rb, 128, 0, st>>>(ws, splits, Mo, Nin, taps, dw, accumulate, swapped);
+  const long long pairs = (long long)Mo * Nin;
+  int rb = (int)((pairs + 255) / 256);
+  if (rb > 148 * 8) rb = 148 * 8;
+  switch (taps) {
+    case 9: k_wgrad_reduce<9><<<rb, 256, 0, st>>>(ws, splits, Mo, Nin, dw, accumulate, swapped); break;
+    case 4: k_wgrad_reduce<4><<<rb, 256, 0, st>>>(ws, splits, Mo, Nin, dw, accumulate, swapped); break;
+    case 1: k_wgrad_reduce<1><<<rb, 256, 0, st>>>(ws, splits, Mo, Nin, dw, accumulate, swapped); break;
+    default: set_error("wgrad_reduce: taps must be 1, 4 or 9 (got %d)", taps); return USTRUN_ERR_ARG;
+  }
   return check_launch("wgrad_reduce");
 }
 

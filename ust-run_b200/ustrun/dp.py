@@ -46,11 +46,17 @@ class GradBuckets:
     def reset(self):
         self.pending = [set(m) for m in self.members]
         self.launched = [False] * len(self.ranges)
+        self.streams = [dict() for _ in self.ranges]
         self.works = []
 
-    def mark(self, i: int):
+    def mark(self, i: int, stream=None):
+        """``stream``: the stream tensor i's gradient kernel was enqueued on (weight gradients run on the
+        engine's side stream, BatchNorm parameter gradients on the main one); the bucket waits for every
+        stream that produced one of its members."""
         b = self.bucket_of[i]
         self.pending[b].discard(i)
+        if stream is not None:
+            self.streams[b][stream.cuda_stream] = stream
         if not self.pending[b] and not self.launched[b]:
             self._launch(b)
 
@@ -59,10 +65,15 @@ class GradBuckets:
         self.launched[b] = True
         view = self.flat[s:e]
         if self.comm_stream is not None:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
+            producers = list(self.streams[b].values()) or [torch.cuda.current_stream()]
+            events = []
+            for st in producers:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events.append(ev)
             with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ev)
+                for ev in events:
+                    self.comm_stream.wait_event(ev)
                 self.works.append(dist.all_reduce(view, group=self.group, async_op=True))
         else:
             self.works.append(dist.all_reduce(view, group=self.group, async_op=True))
@@ -186,9 +197,10 @@ class DataParallel:
         requested tensor's kernel is then already in the stream, so its bucket may go."""
         if not last_branch or self.world == 1:
             return
+        cur = torch.cuda.current_stream() if torch.cuda.is_available() else None
         if self._last_requested is not None:
-            self.buckets.mark(self._last_requested)
-        self._last_requested = self._index[id(param)]
+            self.buckets.mark(*self._last_requested)
+        self._last_requested = (self._index[id(param)], cur)
 
     def finish_step(self, opt) -> float:
         if self.world > 1:

@@ -71,6 +71,51 @@ def _profiled(cls, flops, name, *args):
     PROFILE_EVENTS.append((cls, flops, e0, e1))
 
 
+# Weight-gradient GEMMs are off the backward critical path (nothing downstream reads dW until the
+# optimiser / all-reduce) and use ~56 registers per thread, so they run on a side stream and share the
+# SMs with the HBM-bound BatchNorm / pooling kernels of the next layers instead of serialising with them.
+_WGRAD_OVERLAP = os.environ.get("USTRUN_WGRAD_OVERLAP", "1") == "1"
+_SIDE: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def set_wgrad_overlap(flag: bool) -> None:
+    global _WGRAD_OVERLAP
+    _WGRAD_OVERLAP = bool(flag)
+
+
+def _side_stream():
+    if not _WGRAD_OVERLAP or PROFILE_EVENTS is not None or torch.cuda.is_current_stream_capturing():
+        return None
+    dev = torch.cuda.current_device()
+    st = _SIDE.get(dev)
+    if st is None:
+        st = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def on_side_stream(fn: Callable, tensors) -> None:
+    """Run ``fn`` (which enqueues kernels reading ``tensors``) on the weight-gradient stream, ordered after
+    everything enqueued so far on the current stream."""
+    side = _side_stream()
+    if side is None:
+        fn()
+        return
+    ev = torch.cuda.Event()
+    ev.record()
+    with torch.cuda.stream(side):
+        side.wait_event(ev)
+        fn()
+    for t in tensors:
+        t.record_stream(side)           # the caching allocator must not recycle them under the side stream
+
+
+def join_side_stream() -> None:
+    """Make the current stream wait for all weight-gradient kernels (before the optimiser / all-reduce)."""
+    st = _SIDE.get(torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if st is not None:
+        torch.cuda.current_stream().wait_stream(st)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -164,6 +209,7 @@ class Ctx:
         for fn in reversed(self.tape):
             fn(sink)
         self.tape = []
+        join_side_stream()               # weight gradients are complete for whoever runs next on this stream
 
 
 # --------------------------------------------------------------------------------------------
@@ -344,8 +390,10 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
             draw = raw.like()
             _call("ustrun_bn_bwd_apply", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
                   act, draw.ptr, draw.ld, raw.dtype_code, raw.npix, cout, _stream())
-            dw, acc_w = sink.get(conv.weight)
-            _wgrad(draw, x, dw, acc_w, ks)
+            def wgrad_fn():
+                dw, acc_w = sink.get(conv.weight)
+                _wgrad(draw, x, dw, acc_w, ks)
+            on_side_stream(wgrad_fn, (draw.t, x.t))
             if conv.bias is not None:
                 dbias, acc = sink.get(conv.bias)          # BN removes the mean: d/dbias == 0 exactly
                 if not acc:
@@ -382,11 +430,13 @@ def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
             G = out.g
             if G is None:
                 return
-            dw, acc = sink.get(up.weight)
-            nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(impl, x.B, x.H, x.W, cin, cout, 2)
-            ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
-            _call("ustrun_convT2x2_wgrad", impl, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code, x.B, x.H, x.W, cin, cout,
-                  _ptr(ws), int(nbytes), _stream())
+            def wgrad_fn():
+                dw, acc = sink.get(up.weight)
+                nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(impl, x.B, x.H, x.W, cin, cout, 2)
+                ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+                _call("ustrun_convT2x2_wgrad", impl, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code, x.B, x.H, x.W, cin, cout,
+                      _ptr(ws), int(nbytes), _stream())
+            on_side_stream(wgrad_fn, (G.t, x.t))
             if up.bias is not None:
                 db, accb = sink.get(up.bias)
                 wsb = torch.empty(L.MAX_PARTS * cout, dtype=torch.float32, device=dev)
@@ -434,11 +484,13 @@ def head_conv(ctx: Ctx, x: Act, conv, packed: PackedConv):
         cpad = cout                                        # narrow NHWC copy of dlogits
         G = Act.new(x.B, x.H, x.W, cpad, dtype=x.t.dtype, device=dev)
         _call("ustrun_nchw_to_nhwc", _ptr(dlogits), G.ptr, G.dtype_code, x.B, cout, x.H, x.W, G.ld, _stream())
-        dw, acc = sink.get(conv.weight)
-        nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(L.SIMT, x.B, x.H, x.W, x.C, cout, ks)
-        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
-        _call("ustrun_conv_wgrad", L.SIMT, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code, x.B, x.H, x.W, x.C, cout, ks,
-              _ptr(ws), int(nbytes), _stream())
+        def wgrad_fn():
+            dw, acc = sink.get(conv.weight)
+            nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(L.SIMT, x.B, x.H, x.W, x.C, cout, ks)
+            ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+            _call("ustrun_conv_wgrad", L.SIMT, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code, x.B, x.H, x.W, x.C, cout, ks,
+                  _ptr(ws), int(nbytes), _stream())
+        on_side_stream(wgrad_fn, (G.t, x.t))
         if conv.bias is not None:
             db, accb = sink.get(conv.bias)
             wsb = torch.empty(L.MAX_PARTS * cout, dtype=torch.float32, device=dev)
