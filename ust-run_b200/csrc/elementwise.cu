@@ -243,7 +243,7 @@ k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __restrict__ x, int l
                 const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ scale, const float* __restrict__ shift, int act, long long npix,
                 int C, float* __restrict__ partials) {
-  extern __shared__ float sm[];   // [16][256]
+  extern __shared__ float sm[];   // [8][256]
   const int CG = C >> 3;
   const int tid = threadIdx.x;
   float acc[16];
@@ -268,19 +268,34 @@ k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __restrict__ x, int l
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 16; ++k) sm[k * 256 + tid] = acc[k];
-  __syncthreads();
+  // block totals in two phases through one 8 KB buffer (sum g', then sum g'*x): with <= 9 KB of shared memory two of
+  // these blocks fit next to a resident weight-gradient CTA (200 KB) that runs concurrently on the side stream
   const int lanes = 256 / CG;
-  for (int c = tid; c < C; c += 256) {
-    const int cg = c >> 3, k = c & 7;
-    float s1 = 0.f, s2 = 0.f;
-    for (int l = 0; l < lanes; ++l) {
-      s1 += sm[k * 256 + l * CG + cg];
-      s2 += sm[(8 + k) * 256 + l * CG + cg];
+  float s1r[4], s2r[4];                  // C <= 1024: a thread finalises at most 4 channels
+#pragma unroll
+  for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[k * 256 + tid] = acc[ph * 8 + k];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + i * 256;
+      float s = 0.f;
+      if (c < C) {
+        const int cg = c >> 3, k = c & 7;
+        for (int l = 0; l < lanes; ++l) s += sm[k * 256 + l * CG + cg];
+      }
+      if (ph == 0) s1r[i] = s; else s2r[i] = s;
     }
-    partials[(size_t)blockIdx.x * 2 * C + c] = s1;
-    partials[(size_t)blockIdx.x * 2 * C + C + c] = rstd[c] * (s2 - mean[c] * s1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tid + i * 256;
+    if (c < C) {
+      partials[(size_t)blockIdx.x * 2 * C + c] = s1r[i];
+      partials[(size_t)blockIdx.x * 2 * C + C + c] = rstd[c] * (s2r[i] - mean[c] * s1r[i]);
+    }
   }
 }
 
@@ -309,7 +324,7 @@ __global__ void k_bn_bwd_finalize(const float* __restrict__ partials, int nparts
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_bn_bwd_apply(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ldx, const float* __restrict__ mean,
                const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
                const float* __restrict__ coef, int act, T* __restrict__ dx, int lddx, long long npix, int C) {
@@ -319,14 +334,24 @@ k_bn_bwd_apply(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ld
   const long long n = npix * CG, stride = (long long)gridDim.x * blockDim.x;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int cg = (int)(i % CG);
-  float mu[8], rs[8], sc[8], sh[8], a[8], b[8], d[8];
-  Vec8<float>::load(mean + cg * 8, mu);
-  Vec8<float>::load(rstd + cg * 8, rs);
+  // dx = a*(g' - b - xhat*d), xhat = (x - mean)*rstd  ==  a*g' + cx*x + c0 with cx = -a*d*rstd, c0 = -cx*mean - a*b:
+  // five per-channel vectors stay live in the loop (a, cx, c0 and scale/shift for the activation mask)
+  float sc[8], sh[8], a[8], cx[8], c0[8];
+  {
+    float mu[8], rs[8], b[8], d[8];
+    Vec8<float>::load(mean + cg * 8, mu);
+    Vec8<float>::load(rstd + cg * 8, rs);
+    Vec8<float>::load(coef + cg * 8, a);
+    Vec8<float>::load(coef + C + cg * 8, b);
+    Vec8<float>::load(coef + 2 * C + cg * 8, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      cx[k] = -a[k] * d[k] * rs[k];
+      c0[k] = -cx[k] * mu[k] - a[k] * b[k];
+    }
+  }
   Vec8<float>::load(scale + cg * 8, sc);
   Vec8<float>::load(shift + cg * 8, sh);
-  Vec8<float>::load(coef + cg * 8, a);
-  Vec8<float>::load(coef + C + cg * 8, b);
-  Vec8<float>::load(coef + 2 * C + cg * 8, d);
   const long long pstep = stride / CG;             // stride % CG == 0: no division inside the loop
   (void)n;
 #pragma unroll 2
@@ -336,9 +361,8 @@ k_bn_bwd_apply(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ld
     Vec8<T>::load(x + p * ldx + cg * 8, xv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float gp = gv[k] * act_grad(fmaf(xv[k], sc[k], sh[k]), act);
-      float xh = (xv[k] - mu[k]) * rs[k];
-      o[k] = a[k] * (gp - b[k] - xh * d[k]);
+      const float gp = gv[k] * act_grad(fmaf(xv[k], sc[k], sh[k]), act);
+      o[k] = fmaf(a[k], gp, fmaf(cx[k], xv[k], c0[k]));
     }
     Vec8<T>::store(dx + p * lddx + cg * 8, o);
   }
@@ -617,7 +641,7 @@ int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const f
   if (grid < 1) grid = 1;
   if (grid > 148 * 6) grid = 148 * 6;                                // two waves of 3 resident blocks per SM
   *nparts_host = grid;
-  DISPATCH_DTYPE(dtype, (k_bn_bwd_reduce<T><<<grid, 256, 256 * 16 * sizeof(float), (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, (k_bn_bwd_reduce<T><<<grid, 256, 256 * 8 * sizeof(float), (cudaStream_t)stream>>>(
                             (const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale, shift, act, npix, C, partials)));
   return check_launch("bn_bwd_reduce");
 }

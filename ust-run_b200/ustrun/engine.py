@@ -75,6 +75,7 @@ def _profiled(cls, flops, name, *args):
 # optimiser / all-reduce) and use ~56 registers per thread, so they run on a side stream and share the
 # SMs with the HBM-bound BatchNorm / pooling kernels of the next layers instead of serialising with them.
 _WGRAD_OVERLAP = os.environ.get("USTRUN_WGRAD_OVERLAP", "1") == "1"
+_WGRAD_AFTER_DGRAD = os.environ.get("USTRUN_WGRAD_AFTER_DGRAD", "0") == "1"
 _SIDE: Dict[int, "torch.cuda.Stream"] = {}
 
 
@@ -114,6 +115,22 @@ def join_side_stream() -> None:
     st = _SIDE.get(torch.cuda.current_device()) if torch.cuda.is_available() else None
     if st is not None:
         torch.cuda.current_stream().wait_stream(st)
+
+
+def reserve_pool(nbytes: Optional[int] = None, fraction: float = 0.5, cap: int = 96 << 30) -> int:
+    """Seed torch's caching allocator with one large free block (default: half of the free HBM, at most 96 GiB).
+    The engine allocates every activation through torch; without this the pool grows by cudaMalloc (a device
+    synchronisation each) over the first ~20 steps -- longer with the weight-gradient side stream, whose
+    ``record_stream`` holds blocks back -- and those steps run 2-3x slower.  Returns the bytes reserved."""
+    L.require_device()
+    if nbytes is None:
+        free, _total = torch.cuda.mem_get_info()
+        nbytes = min(int(free * fraction), cap)
+    nbytes = max(int(nbytes), 0)
+    if nbytes:
+        blk = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        del blk                      # stays cached; later requests split it
+    return nbytes
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -390,18 +407,21 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
             draw = raw.like()
             _call("ustrun_bn_bwd_apply", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
                   act, draw.ptr, draw.ld, raw.dtype_code, raw.npix, cout, _stream())
-            def wgrad_fn():
-                dw, acc_w = sink.get(conv.weight)
-                _wgrad(draw, x, dw, acc_w, ks)
-            on_side_stream(wgrad_fn, (draw.t, x.t))
             if conv.bias is not None:
                 dbias, acc = sink.get(conv.bias)          # BN removes the mean: d/dbias == 0 exactly
                 if not acc:
                     dbias.zero_()
+            def wgrad_fn():
+                dw, acc_w = sink.get(conv.weight)
+                _wgrad(draw, x, dw, acc_w, ks)
+            if not _WGRAD_AFTER_DGRAD:
+                on_side_stream(wgrad_fn, (draw.t, x.t))
             if x.needs_grad:
                 gx = Act.new(x.B, x.H, x.W, x.C, dtype=x.t.dtype, device=dev)
                 _raw_conv(draw, wd, None, gx, ks)
                 _assign_grad(x, gx)
+            if _WGRAD_AFTER_DGRAD:
+                on_side_stream(wgrad_fn, (draw.t, x.t))
 
         ctx.tape.append(bwd)
         y.needs_grad = True
