@@ -199,6 +199,17 @@ int ustrun_sgd_ema_multi(const ustrun_param_t* table, const int* blk_tensor, con
                          float lr, float momentum, float weight_decay, float alpha, float grad_scale, int do_sgd,
                          int do_ema, void* stream);
 
+/* ---- frequency-domain style mix -------------------------------------------
+ * Replaces the per-sample host loop of train.py:628-636 (extract_amp_spectrum train.py:158-165,
+ * low_freq_mutate_np :167-187, source_to_target_freq :189-207): out[n] = clip(Re ifft2(amp'(n) * exp(i*phase_src)), 0, 255)
+ * / 127.5 - 1 with amp' = amp_src*(1-ratio[n]) + amp_trg*ratio[n] inside the centred window of half-width
+ * b = floor(min(H,W)*L) and amp_src outside.  src (the CutMix partner, mix_img), trg (ulb_x_w), out: fp32 NCHW in
+ * [-1,1]; ratio: one float64 per sample (the host's random.uniform(0, iter/max_iter), train.py:180).  float64
+ * arithmetic on the device; 2b+1 <= 25.  workspace: ustrun_fft_amp_mix_workspace_bytes(). */
+long long ustrun_fft_amp_mix_workspace_bytes(int N, int C, int H, int W, double L);
+int ustrun_fft_amp_mix(const float* src, const float* trg, const double* ratio, double L, float* out, int N, int C, int H, int W,
+                       void* workspace, long long ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

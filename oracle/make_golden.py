@@ -261,9 +261,62 @@ def case_step(model, branch, n_channels, n_classes, hw, B, iter_num, bank):
     print(f"{name}: loss={loss.item():.6f} mask_mean={comp['mask'].mean().item():.3f} ok")
 
 
+def _reference_fft_functions():
+    """train.py cannot be imported (argparse + dataset dispatch at import time), so the three FFT
+    helpers are lifted out of its source with ``ast`` at generation time and executed unmodified; only
+    ``random.uniform`` is replaced by a stub that replays the recorded ratios."""
+    import ast
+    src = open(os.path.join(REF, "train.py")).read()
+    tree = ast.parse(src)
+    want = ("extract_amp_spectrum", "low_freq_mutate_np", "source_to_target_freq")
+    code = "\n\n".join(ast.get_source_segment(src, n) for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want)
+
+    class _Random:
+        ratios = []
+
+        @classmethod
+        def uniform(cls, lo, hi):
+            return cls.ratios.pop(0)
+
+    ns = {"np": np, "random": _Random}
+    exec(compile(code, os.path.join(REF, "train.py"), "exec"), ns)
+    return ns, _Random
+
+
+def case_fft_mix():
+    """Frequency-domain style mix (train.py:158-207,628-636): the reference's own functions vs the oracle."""
+    from oracle import fft_mix_ref as Fm
+    ns, rnd = _reference_fft_functions()
+    rng = np.random.RandomState(SEED)
+    fx = {}
+    for tag, (N, C, H, W, L) in {"c1_48x48_L0p1": (2, 1, 48, 48, 0.1), "c3_64x40_L0p05": (2, 3, 64, 40, 0.05),
+                                 "c1_96x96_L0p01": (1, 1, 96, 96, 0.01), "c1_128x160_L0p03": (2, 1, 128, 160, 0.03)}.items():
+        mix_img = torch.from_numpy(rng.uniform(-1, 1, (N, C, H, W)).astype(np.float32))
+        ulb = torch.from_numpy(rng.uniform(-1, 1, (N, C, H, W)).astype(np.float32))
+        ratios = rng.uniform(0, 1, N).tolist()
+        rnd.ratios = list(ratios)
+        out = []
+        for i in range(N):                                            # train.py:629-633 verbatim
+            amp_trg = ns["extract_amp_spectrum"]((ulb[i].cpu().numpy() + 1) * 127.5)
+            img_freq = ns["source_to_target_freq"](((mix_img[i] + 1) * 127.5).cpu().numpy(), amp_trg, L=L, degree=1.0)
+            img_freq = np.clip(img_freq, 0, 255).astype(np.float32)
+            out.append(img_freq)
+        ref = torch.tensor(np.array(out), dtype=torch.float32) / 127.5 - 1   # train.py:634-635
+        got = Fm.move_transx(mix_img.numpy(), ulb.numpy(), ratios, L)
+        assert np.array_equal(ref.numpy(), got), f"fft mix oracle differs from the reference ({tag})"
+        fx[f"{tag}/mix_img"], fx[f"{tag}/ulb_x_w"] = mix_img.numpy(), ulb.numpy()
+        fx[f"{tag}/ratio"], fx[f"{tag}/L"], fx[f"{tag}/out"] = np.asarray(ratios), np.asarray(L), ref.numpy()
+    np.savez_compressed(os.path.join(OUT, "fft_mix.npz"), **fx)
+    print("fft_mix: reference == oracle bit-for-bit on", len(fx) // 5, "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if len(sys.argv) > 1 and sys.argv[1] == "fft":
+        case_fft_mix()
+        return
+    case_fft_mix()
     case_losses()
     case_unet_a(1, 2, 32, 2)
     case_unet_a(3, 3, 32, 2)

@@ -145,3 +145,17 @@ def test_oracle_live_against_reference():
             "print('live-ok')\n") % os.path.dirname(GOLDEN.rstrip('/')).rsplit('/tests', 1)[0]
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "live-ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_fft_mix_oracle_reproduces_reference_fixture():
+    """oracle/fft_mix_ref.py against tests/golden/fft_mix.npz (outputs of the reference's own
+    extract_amp_spectrum / low_freq_mutate_np / source_to_target_freq, train.py:158-207, lifted by make_golden)."""
+    from oracle import fft_mix_ref as Fm
+    fx = np.load(os.path.join(GOLDEN, "fft_mix.npz"))
+    tags = sorted({k.split("/")[0] for k in fx.files})
+    assert len(tags) == 4
+    for tag in tags:
+        got = Fm.move_transx(fx[f"{tag}/mix_img"], fx[f"{tag}/ulb_x_w"], fx[f"{tag}/ratio"].tolist(), float(fx[f"{tag}/L"]))
+        assert got.dtype == np.float32
+        # bit-for-bit in the build container; another BLAS/pocketfft build may differ in the last float64 bit
+        assert np.allclose(got, fx[f"{tag}/out"], rtol=0, atol=2e-6), tag

@@ -193,37 +193,50 @@ k_wgrad_simt(const T* __restrict__ a, int lda, const T* __restrict__ bsrc, int l
   }
 }
 
-// dw[(m*Nin + c)*taps + t] (+)= sum_s ws[s][m][t*Nin + c].  One thread per (m, c): its taps*splits loads are all
-// independent (coalesced across the warp along c), and its `taps` results are one contiguous run of the OIHW tensor,
-// so a warp reads/writes 32*taps consecutive floats.  No shared memory, no barriers: the kernel is pure memory-level
-// parallelism (the previous block-per-tile version was latency-bound at ~36 us per call).
+// dw[(m*Nin + c)*taps + t] (+)= sum_s ws[s][m][t*Nin + c].  One WARP per (m, 32 consecutive c): lane = c, so the
+// taps*splits loads of a lane are independent and coalesced along c; the 32 x taps results are transposed through a
+// per-warp shared-memory tile (no block barrier) and leave as ONE contiguous run of 32*taps floats of the OIHW
+// tensor (read-modify-write when accumulating), 128 bytes per store instruction.
 template <int TAPS>
 __global__ void __launch_bounds__(256)
 k_wgrad_reduce(const float* __restrict__ ws, int splits, int Mo, int Nin, float* __restrict__ dw, int accumulate, int swapped) {
-  const long long n = (long long)Mo * Nin * TAPS, pairs = (long long)Mo * Nin;
-  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < pairs; j += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(j / Nin), c = (int)(j - (long long)m * Nin);
+  __shared__ float tile[8][32 * TAPS + 1];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int cchunks = (Nin + 31) >> 5;
+  const long long n = (long long)Mo * Nin * TAPS, groups = (long long)Mo * cchunks;
+  for (long long g = (long long)blockIdx.x * 8 + wrp; g < groups; g += (long long)gridDim.x * 8) {
+    const int m = (int)(g / cchunks), c0 = (int)(g - (long long)m * cchunks) * 32;
+    const int nc = min(32, Nin - c0);
     float acc[TAPS];
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) acc[t] = 0.f;
-    const float* src = ws + ((size_t)m * TAPS) * Nin + c;
-    for (int k = 0; k < splits; ++k) {
+    if (lane < nc) {
+      const float* src = ws + ((size_t)m * TAPS) * Nin + c0 + lane;
+      for (int k = 0; k < splits; ++k) {
 #pragma unroll
-      for (int t = 0; t < TAPS; ++t) acc[t] += src[(size_t)k * n + (size_t)t * Nin];
+        for (int t = 0; t < TAPS; ++t) acc[t] += src[(size_t)k * n + (size_t)t * Nin];
+      }
     }
-    float* dst = swapped ? dw + ((size_t)c * Mo + m) * TAPS : dw + (size_t)j * TAPS;   // swapped: ws rows are input channels
-    if (accumulate) {
+    if (swapped) {                                    // ws rows are input channels: dw[(c*Mo + m)*taps + t] (small layers only)
+      if (lane < nc) {
+        float* dst = dw + ((size_t)(c0 + lane) * Mo + m) * TAPS;
 #pragma unroll
-      for (int t = 0; t < TAPS; ++t) acc[t] += dst[t];
+        for (int t = 0; t < TAPS; ++t) dst[t] = (accumulate ? dst[t] : 0.f) + acc[t];
+      }
+      continue;
     }
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) dst[t] = acc[t];
+    for (int t = 0; t < TAPS; ++t) tile[wrp][lane * TAPS + t] = acc[t];
+    __syncwarp();
+    float* dst = dw + ((size_t)m * Nin + c0) * TAPS;
+    for (int i = lane; i < nc * TAPS; i += 32) dst[i] = (accumulate ? dst[i] : 0.f) + tile[wrp][i];
+    __syncwarp();
   }
 }
 
 int launch_wgrad_reduce(const float* ws, int splits, int Mo, int Nin, int taps, float* dw, int accumulate, cudaStream_t st, int swapped) {
-  const long long pairs = (long long)Mo * Nin;
-  int rb = (int)((pairs + 255) / 256);
+  const long long groups = (long long)Mo * ((Nin + 31) / 32);
+  int rb = (int)((groups + 7) / 8);
   if (rb > 148 * 8) rb = 148 * 8;
   switch (taps) {
     case 9: k_wgrad_reduce<9><<<rb, 256, 0, st>>>(ws, splits, Mo, Nin, dw, accumulate, swapped); break;

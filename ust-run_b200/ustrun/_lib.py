@@ -69,6 +69,7 @@ _SIGS = {
     "ustrun_bn_finalize_peer": [p, i32, i32, f64, p, p, p, p, p, p, f32, f32, p, p, p, p, p, i32, i32, C.c_uint, p, p, p],
     "ustrun_bn_bwd_finalize_peer": [p, i32, i32, f64, p, p, p, p, i32, p, p, i32, i32, C.c_uint, p, p, p],
     "ustrun_sgd_ema_multi": [p, p, p, i32, f32, f32, f32, f32, f32, i32, i32, p],
+    "ustrun_fft_amp_mix": [p, p, p, f64, p, i32, i32, i32, i32, p, i64, p],
 }
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
@@ -81,8 +82,11 @@ lib.ustrun_conv_wgrad_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, 
 
 lib.ustrun_peer_buffer_bytes.restype = i64
 lib.ustrun_peer_buffer_bytes.argtypes = []
+lib.ustrun_fft_amp_mix_workspace_bytes.restype = i64
+lib.ustrun_fft_amp_mix_workspace_bytes.argtypes = [i32, i32, i32, i32, f64]
 
-EXPORTS = sorted(list(_SIGS) + ["ustrun_last_error_string", "ustrun_conv_wgrad_workspace_bytes", "ustrun_peer_buffer_bytes"])
+EXPORTS = sorted(list(_SIGS) + ["ustrun_last_error_string", "ustrun_conv_wgrad_workspace_bytes", "ustrun_peer_buffer_bytes",
+                                 "ustrun_fft_amp_mix_workspace_bytes"])
 
 
 def last_error() -> str:

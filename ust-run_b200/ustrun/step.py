@@ -89,12 +89,13 @@ def mix_input(a, b, box_u8, b_index=None) -> E.Act:
 class SSLTrainer:
     def __init__(self, model, ema_model, n_classes, branch="softmax", base_lr=0.03, max_iterations=30000, threshold=0.95,
                  consistency=1.0, consistency_rampup=200.0, ema_decay=0.99, momentum=0.9, weight_decay=1e-4, dp=None,
-                 forward_kwargs=None):
+                 forward_kwargs=None, fft_window=0.01):
         self.model, self.ema_model = model, ema_model
         self.n_classes, self.branch = n_classes, branch
         self.base_lr, self.lr, self.max_iterations = base_lr, base_lr, max_iterations
         self.threshold, self.consistency, self.consistency_rampup, self.ema_decay = threshold, consistency, consistency_rampup, ema_decay
         self.iter_num = 0
+        self.fft_window = fft_window          # --LB (train.py:76): half-width of the amplitude window as a fraction of min(H, W)
         self.dp = dp
         self.forward_kwargs = forward_kwargs or {}
         self.params = list(model.parameters())
@@ -136,7 +137,8 @@ class SSLTrainer:
     # -- the step ----------------------------------------------------------------------------
     def step(self, batch, lq=None, keep_logits=False):
         """batch: lb_x [Bl,C,H,W] fp32, lb_mask ([Bl,H,W] int | [Bl,C,H,W] float), ulb_w, ulb_s,
-        move_transx [Bu,C,H,W], box [Bu,H,W] {0,1}, choice [Bu] int, cut_img [Nc,C,H,W],
+        move_transx [Bu,C,H,W] (or, instead, mix_ratio [Bu]: the style mix then runs on the device),
+        box [Bu,H,W] {0,1}, choice [Bu] int, cut_img [Nc,C,H,W],
         cut_label, cut_mask (labelled batch + confidence bank).  ``lq``: optional [1,C,H,W] image
         whose student forward only updates BN running statistics (train.py:740).
         Returns device tensors (losses, compositions); nothing is copied to the host."""
@@ -147,6 +149,12 @@ class SSLTrainer:
         box_u8 = as_u8(b["box"]).contiguous()
         inv_box = 1 - box_u8
         choice_i = b["choice"].to(device=dev, dtype=torch.int32).contiguous()
+        if "move_transx" not in b:
+            # frequency-domain style mix on the device (train.py:628-636): the host only supplies
+            # its random blend ratio per sample (train.py:180) instead of running fft2/ifft2 in numpy
+            from .fft_mix import amp_mix
+            b = dict(b)
+            b["move_transx"] = amp_mix(b["cut_img"].float()[choice_i.long()], b["ulb_w"], b["mix_ratio"], self.fft_window)
         # 1. teacher
         _, t1, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], None, None), False)
         _, t2, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], b["cut_img"], box_u8, choice_i), False)
