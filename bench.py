@@ -238,9 +238,26 @@ def run_ours(args):
             for n, v in classes.items()}
     top = max(kern, key=lambda n: kern[n]["ms_per_step"]) if kern else None
     peak_tf = pk["tf_sustained"]
+    # all tensor-core conv launches of a step together (forward, dgrad, wgrad, transposed convs)
+    tc = [v for n, v in classes.items() if n.startswith("tc_")]
+    tc_flops, tc_ms = sum(v[0] for v in tc), sum(v[1] for v in tc)
+    conv_layers = {"tflops": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None, "ms_per_step": tc_ms / prof_steps,
+                   "frac_of_sustained_peak": tc_flops / (tc_ms * 1e-3) / 1e12 / pk["tf_sustained"] if tc_ms > 0 else None,
+                   "frac_of_burst_peak": tc_flops / (tc_ms * 1e-3) / 1e12 / pk["tf_burst"] if tc_ms > 0 else None}
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (tools/ncu_traffic.py)
+    traffic, traffic_note = None, "no capture committed"
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_tc_conv_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_note = (f"mean over {tj['launches']} k_tc_conv launches (13 layers x fwd/dgrad, cfg2 shapes) of dram__bytes_read+write from {tj['source']}; "
+                        f"algorithmic {tj['algorithmic_bytes_per_launch']:.3e} B/launch, ratio {tj['ratio']:.2f}")
     roofline = {"bound": "tensor", "kernel": top, "achieved": kern[top]["tflops"] if top else None, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (kern[top]["tflops"] / peak_tf) if top else None, "traffic": None,
+                "frac": (kern[top]["tflops"] / peak_tf) if top else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
+                "flops_per_launch": (classes[top][0] / classes[top][2]) if top else None,
+                "us_per_launch": (classes[top][1] * 1e3 / classes[top][2]) if top else None,
+                "conv_layers": conv_layers,
                 "step_conv_tflops": step_flops / (ms * 1e-3) / 1e12, "step_frac_of_peak": step_flops / (ms * 1e-3) / 1e12 / peak_tf,
                 "kernels": kern}
     cpu = cpu_baseline(args, bounded=True)
