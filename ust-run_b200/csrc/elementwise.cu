@@ -62,6 +62,22 @@ __global__ void k_nchw_to_nhwc(const float* __restrict__ src, T* __restrict__ ds
     if (p < HW && c < C) dst[((size_t)b * HW + p) * ld + c] = from_f<T>(tile[threadIdx.x][i]);
   }
 }
+// C <= 8 (logit gradients, 1..4-channel images): one thread per pixel, plane reads coalesced across the warp,
+// the C outputs of a pixel written back to back (the 32x32 tile kernel above would use 2 of its 32 channel lanes)
+template <typename T, int C>
+__global__ void __launch_bounds__(256)
+k_nchw_to_nhwc_small(const float* __restrict__ src, T* __restrict__ dst, long long HW, int ld, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    float v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = src[(b * C + c) * HW + p];
+    T* d = dst + i * ld;
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[c] = from_f<T>(v[c]);
+  }
+}
+
 template <typename T>
 __global__ void k_nhwc_to_nchw(const T* __restrict__ src, float* __restrict__ dst, int C, int HW, int ld) {
   __shared__ float tile[32][33];
@@ -575,6 +591,14 @@ int ustrun_device_supported(void) {
 
 int ustrun_nchw_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int H, int W, int ld_dst, void* stream) {
   USTRUN_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0 && ld_dst >= C, "nchw_to_nhwc: bad args");
+  if (C <= 4) {
+    const long long HW = (long long)H * W, total = (long long)B * HW;
+    const int g = grid_for(total, 256);
+#define SMALL(CV) DISPATCH_DTYPE(dtype, (k_nchw_to_nhwc_small<T, CV><<<g, 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, HW, ld_dst, total)))
+    switch (C) { case 1: SMALL(1); break; case 2: SMALL(2); break; case 3: SMALL(3); break; default: SMALL(4); break; }
+#undef SMALL
+    return check_launch("nchw_to_nhwc_small");
+  }
   dim3 grid(ceil_div((long long)H * W, 32), ceil_div(C, 32), B), block(32, 8);
   DISPATCH_DTYPE(dtype, (k_nchw_to_nhwc<T><<<grid, block, 0, (cudaStream_t)stream>>>(src, (T*)dst, C, H * W, ld_dst)));
   return check_launch("nchw_to_nhwc");

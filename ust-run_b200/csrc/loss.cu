@@ -222,10 +222,13 @@ __global__ void k_ce_dice_finalize(const float* __restrict__ partials, int npart
                                    const float* __restrict__ class_weight, float* __restrict__ coef, float* __restrict__ loss_out) {
   __shared__ double tot[3 * MAXC + 1];
   const int nacc = 3 * C + 1;
-  if (threadIdx.x < nacc) {
+  // one warp per accumulator, lanes stride over the partial rows (fixed order: deterministic)
+  for (int a = threadIdx.x >> 5; a < nacc; a += blockDim.x >> 5) {
     double s = 0.0;
-    for (int r = 0; r < nparts; ++r) s += (double)partials[(size_t)r * nacc + threadIdx.x];
-    tot[threadIdx.x] = s;
+    for (int r = threadIdx.x & 31; r < nparts; r += 32) s += (double)partials[(size_t)r * nacc + a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) tot[a] = s;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -315,10 +318,12 @@ __global__ void __launch_bounds__(256) k_bce_dice_pass1(const float* __restrict_
 __global__ void k_bce_dice_finalize(const float* __restrict__ partials, int nparts, double n, float ce_w, float dice_w,
                                     float* __restrict__ coef, float* __restrict__ loss_out) {
   __shared__ double tot[4];
-  if (threadIdx.x < 4) {
+  for (int a = threadIdx.x >> 5; a < 4; a += blockDim.x >> 5) {
     double s = 0.0;
-    for (int r = 0; r < nparts; ++r) s += (double)partials[(size_t)r * 4 + threadIdx.x];
-    tot[threadIdx.x] = s;
+    for (int r = threadIdx.x & 31; r < nparts; r += 32) s += (double)partials[(size_t)r * 4 + a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) tot[a] = s;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -446,7 +451,7 @@ int ustrun_ce_dice_softmax_partials(const float* logits, const uint8_t* target, 
 int ustrun_ce_dice_softmax_finalize(const float* workspace, int nparts, int C, double npix_total, float ce_w, float dice_w,
                                     const float* class_weight, float* coef, float* loss_out, void* stream) {
   USTRUN_REQUIRE(workspace && nparts > 0 && C >= 2 && C <= 8 && npix_total > 0 && coef && loss_out, "ce_dice_softmax_finalize: bad args");
-  k_ce_dice_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, nparts, C, npix_total, ce_w, dice_w, class_weight, coef, loss_out);
+  k_ce_dice_finalize<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, nparts, C, npix_total, ce_w, dice_w, class_weight, coef, loss_out);
   return check_launch("ce_dice_softmax_finalize");
 }
 int ustrun_ce_dice_softmax_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W, float ce_w,
@@ -478,7 +483,7 @@ int ustrun_bce_dice_sigmoid_partials(const float* logits, const uint8_t* target,
 int ustrun_bce_dice_sigmoid_finalize(const float* workspace, int nparts, double nelem_total, float ce_w, float dice_w, float* coef,
                                      float* loss_out, void* stream) {
   USTRUN_REQUIRE(workspace && nparts > 0 && nelem_total > 0 && coef && loss_out, "bce_dice_sigmoid_finalize: bad args");
-  k_bce_dice_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, nparts, nelem_total, ce_w, dice_w, coef, loss_out);
+  k_bce_dice_finalize<<<1, 128, 0, (cudaStream_t)stream>>>(workspace, nparts, nelem_total, ce_w, dice_w, coef, loss_out);
   return check_launch("bce_dice_sigmoid_finalize");
 }
 int ustrun_bce_dice_sigmoid_fwd(const float* logits, const uint8_t* target, const uint8_t* mask, int B, int C, int H, int W, float ce_w,

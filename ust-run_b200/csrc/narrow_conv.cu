@@ -5,6 +5,8 @@
 //   * their weight gradients (one operand 8..256 channels wide, the other <= 8) -> k_wgrad_narrow
 // A tensor-core tile would be >90 % padding here; these kernels stream the wide tensor once with
 // 128-bit accesses and keep the small operand / weights in shared memory or registers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ustrun {
@@ -186,6 +188,124 @@ k_conv_narrow_quad(const T* __restrict__ x, int ldx, const T* __restrict__ wp, c
       float s = 0.f;
       for (int l = 0; l < pgs; ++l) s += red[(l * CG + (c >> 3)) * 16 + which * 8 + (c & 7)];
       partials[(size_t)blockIdx.x * 2 * Cout + o] = s;
+    }
+  }
+}
+
+// ---- warp-level tensor-core variant of the first convolution (bf16, 3x3, Cin <= 4) ------------------------------
+// K = 9*Cin <= 36 is far too short for a tcgen05 tile (the A operand would have to be materialised as an im2col
+// buffer first), and the layer is HBM-bound (write 128 B per pixel) -- the CUDA-core kernel above needs 576 FMAs per
+// pixel and ends up issue-bound at ~4x the memory time.  Here a warp owns 16 consecutive pixels of an image row and
+// runs mma.sync.m16n8k16 (bf16 in, fp32 accumulate): the A fragment is gathered straight from the 3x3 neighbourhood
+// with predicated 2-byte loads (the input is tiny and L1-resident), the weights live in registers as B fragments,
+// the 16 x Cout tile is transposed through a warp-private shared tile and stored as full 16-byte vectors, and the
+// BatchNorm partial sums accumulate per thread and are reduced once per block.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+template <int CIN, int NT>          // NT = Cout / 8
+__global__ void __launch_bounds__(256)
+k_conv_first_mma(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias,
+                 __nv_bfloat16* __restrict__ y, int ldy, int B, int H, int W, float* __restrict__ partials) {
+  constexpr int K = 9 * CIN, KS = (K + 15) / 16, COUT = NT * 8, PITCH = COUT + 8;       // staging row pitch in bf16 (+16 B: bank spread)
+  __shared__ __align__(16) __nv_bfloat16 stg[8][16 * PITCH];
+  __shared__ float red[8][2 * COUT];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  // B fragments: B[k][n] = w[co = 8j + g][k]; b0 = {k = 16s + 2tig, +1}, b1 = {k = 16s + 2tig + 8, +9}
+  uint32_t bf[NT][KS][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int s_ = 0; s_ < KS; ++s_)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int k0 = 16 * s_ + 2 * tig + 8 * hh;
+        const __nv_bfloat16* wr = wp + (size_t)(8 * j + g) * K;
+        bf[j][s_][hh] = pack_bf16(k0 < K ? wr[k0] : zero, k0 + 1 < K ? wr[k0 + 1] : zero);
+      }
+  float bs[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { bs[j][0] = bias ? bias[8 * j + 2 * tig] : 0.f; bs[j][1] = bias ? bias[8 * j + 2 * tig + 1] : 0.f; }
+  float ssum[NT][2], ssq[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { ssum[j][0] = ssum[j][1] = 0.f; ssq[j][0] = ssq[j][1] = 0.f; }
+
+  const int tiles_w = W >> 4;
+  const long long ntiles = (long long)B * H * tiles_w;
+  for (long long tl = (long long)blockIdx.x * 8 + wrp; tl < ntiles; tl += (long long)gridDim.x * 8) {
+    int tw, h_, b_;
+    pix_decomp(tl, tiles_w, H, b_, h_, tw);
+    const int w0 = tw << 4;
+    // A fragments: A[r][k] = x[b, h + dy - 1, w0 + r + dx - 1, ci], k = (dy*3 + dx)*CIN + ci
+    uint32_t af[KS][4];
+#pragma unroll
+    for (int s_ = 0; s_ < KS; ++s_)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {              // q: (row half, k half) = a0:(g, lo) a1:(g+8, lo) a2:(g, hi) a3:(g+8, hi)
+        const int r = g + 8 * (q & 1);
+        __nv_bfloat16 v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = 16 * s_ + 2 * tig + 8 * (q >> 1) + e;
+          const int t = k / CIN, ci = k - t * CIN, dy = t / 3, dx = t - dy * 3;
+          const int hh = h_ + dy - 1, ww = w0 + r + dx - 1;
+          const bool ok = k < K && hh >= 0 && hh < H && ww >= 0 && ww < W;
+          v[e] = ok ? x[((long long)(b_ * H + hh) * W + ww) * ldx + ci] : zero;
+        }
+        af[s_][q] = pack_bf16(v[0], v[1]);
+      }
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+      for (int s_ = 0; s_ < KS; ++s_) mma_bf16_16816(acc[j], af[s_], bf[j][s_][0], bf[j][s_][1]);
+    }
+    // statistics of the fp32 accumulators (before bias / rounding), then stage the bf16 tile
+    __nv_bfloat16* st = stg[wrp];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      ssum[j][0] += acc[j][0] + acc[j][2]; ssum[j][1] += acc[j][1] + acc[j][3];
+      ssq[j][0] += acc[j][0] * acc[j][0] + acc[j][2] * acc[j][2]; ssq[j][1] += acc[j][1] * acc[j][1] + acc[j][3] * acc[j][3];
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[j][0] + bs[j][0], acc[j][1] + bs[j][1]);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(acc[j][2] + bs[j][0], acc[j][3] + bs[j][1]);
+      *reinterpret_cast<__nv_bfloat162*>(st + g * PITCH + 8 * j + 2 * tig) = lo;
+      *reinterpret_cast<__nv_bfloat162*>(st + (g + 8) * PITCH + 8 * j + 2 * tig) = hi;
+    }
+    __syncwarp();
+    __nv_bfloat16* yrow = y + ((long long)(b_ * H + h_) * W + w0) * ldy;
+#pragma unroll
+    for (int c = lane; c < 16 * NT; c += 32) {            // 16-byte chunks: NT per pixel row
+      const int r = c / NT, cc = c - r * NT;
+      *reinterpret_cast<uint4*>(yrow + (long long)r * ldy + cc * 8) = *reinterpret_cast<const uint4*>(st + r * PITCH + cc * 8);
+    }
+    __syncwarp();
+  }
+  if (partials) {
+    // columns 8j + 2tig (+1) are shared by the 8 lanes with the same tig: xor-reduce over g, then over the 8 warps
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a = ssum[j][e], q = ssq[j][e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+        if (g == 0) { red[wrp][8 * j + 2 * tig + e] = a; red[wrp][COUT + 8 * j + 2 * tig + e] = q; }
+      }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * COUT; o += 256) {
+      float s_ = 0.f;
+#pragma unroll
+      for (int w_ = 0; w_ < 8; ++w_) s_ += red[w_][o];
+      partials[(size_t)blockIdx.x * 2 * COUT + o] = s_;
     }
   }
 }
@@ -405,6 +525,125 @@ k_wgrad_narrow(const T* __restrict__ wide, int ldw, int Cw, const T* __restrict_
   }
 }
 
+// ---- warp-level tensor-core variant of the narrow weight gradients (bf16) -----------------------------------------
+// D[wc][n] = sum_q wide[q][wc] * narrow[q + sgn*tap(n)][nc(n)],  n = tap*CN + nc  (first conv: wide = dY, narrow = x;
+// logits head: wide = x, narrow = dY).  A warp walks 16-pixel row segments: the 16 x Cw slab of the wide tensor goes
+// through a warp-private shared tile (four 16-byte loads per lane) and comes back as m16k16 A fragments via
+// ldmatrix.trans (rows = channels, K = pixels); the B fragments are gathered from the narrow tensor with predicated
+// 2-byte loads; mma.sync.m16n8k16 accumulates in fp32 registers for the whole kernel.  The CUDA-core version spent
+// 72 FMAs per 16 bytes of the wide tensor and ran at ~0.7 TB/s; this one is bound by streaming the wide tensor.
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+template <int CN, int TAPS, int MT>          // MT = Cw / 16 (m-tiles), N = TAPS*CN columns
+__global__ void __launch_bounds__(256)
+k_wgrad_narrow_mma(const __nv_bfloat16* __restrict__ wide, int ldw, const __nv_bfloat16* __restrict__ nar, int ldn, int sgn, int B, int H, int W,
+                   float* __restrict__ ws) {
+  constexpr int N = TAPS * CN, NKT = (N + 7) / 8, CW = MT * 16, PITCH = CW + 8, KSZ = TAPS == 9 ? 3 : 1;
+  __shared__ __align__(16) __nv_bfloat16 stg[8][16 * PITCH];
+  __shared__ float red[MT * 16 * NKT * 8];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  float acc[MT][NKT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NKT; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+  __nv_bfloat16* st = stg[wrp];
+  const int tiles_w = W >> 4;
+  const long long ntiles = (long long)B * H * tiles_w;
+  const long long tstep = (long long)gridDim.x * 8;
+  constexpr int CH = (2 * CW + 31) / 32;                    // 16-byte chunks of the 16 x CW slab per lane
+  uint4 pre[CH];
+  auto load_slab = [&](long long tile) {                     // global -> registers (in flight while the previous slab is consumed)
+    int tw, h_, b_;
+    pix_decomp(tile, tiles_w, H, b_, h_, tw);
+    const __nv_bfloat16* wrow = wide + ((long long)(b_ * H + h_) * W + (tw << 4)) * ldw;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < 2 * CW) {
+        const int r = c / (CW / 8), cc = c - r * (CW / 8);
+        pre[i] = *reinterpret_cast<const uint4*>(wrow + (long long)r * ldw + cc * 8);
+      }
+    }
+  };
+  long long tl = (long long)blockIdx.x * 8 + wrp;
+  if (tl < ntiles) load_slab(tl);
+  for (; tl < ntiles; tl += tstep) {
+    int tw, h_, b_;
+    pix_decomp(tl, tiles_w, H, b_, h_, tw);
+    const int w0 = tw << 4;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < 2 * CW) {
+        const int r = c / (CW / 8), cc = c - r * (CW / 8);
+        *reinterpret_cast<uint4*>(st + r * PITCH + cc * 8) = pre[i];
+      }
+    }
+    if (tl + tstep < ntiles) load_slab(tl + tstep);
+    // B fragments: B[p][n] = nar[b, h + sgn*(dy-1), w0 + p + sgn*(dx-1), nc]; b0: p = 2tig, 2tig+1; b1: p = 2tig+8, +9; n = 8*nt + g
+    uint32_t bfr[NKT][2];
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt) {
+      const int n = 8 * nt + g;
+      const int t = n / CN, nc = n - t * CN;
+      const int dy = KSZ == 3 ? t / 3 - 1 : 0, dx = KSZ == 3 ? t % 3 - 1 : 0;
+      const int hh = h_ + sgn * dy;
+      const bool rowok = n < N && hh >= 0 && hh < H;
+      const __nv_bfloat16* nrow = nar + ((long long)(b_ * H + (rowok ? hh : h_)) * W) * ldn + nc;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        __nv_bfloat16 v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ww = w0 + 2 * tig + 8 * hf + e + sgn * dx;
+          v[e] = (rowok && ww >= 0 && ww < W) ? nrow[(long long)ww * ldn] : zero;
+        }
+        bfr[nt][hf] = pack_bf16(v[0], v[1]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      // A fragment (rows = channels 16m.., K = 16 pixels) from the [pixel][channel] tile: four transposed 8x8 matrices
+      uint32_t af[4];
+      const int mat = lane >> 3, rr = lane & 7;
+      ldmatrix_x4_trans(af, st + (rr + 8 * (mat >> 1)) * PITCH + 16 * m + 8 * (mat & 1));
+#pragma unroll
+      for (int nt = 0; nt < NKT; ++nt) mma_bf16_16816(acc[m][nt], af, bfr[nt][0], bfr[nt][1]);
+    }
+    __syncwarp();
+  }
+  // block total: the 8 warps add their fragments through shared memory (fixed order: deterministic)
+  for (int o = threadIdx.x; o < MT * 16 * NKT * 8; o += 256) red[o] = 0.f;
+  __syncthreads();
+  for (int w_ = 0; w_ < 8; ++w_) {
+    if (wrp == w_) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt) {
+          float* base = red + ((16 * m) * NKT * 8) + 8 * nt;
+          base[(g)*NKT * 8 + 2 * tig] += acc[m][nt][0];
+          base[(g)*NKT * 8 + 2 * tig + 1] += acc[m][nt][1];
+          base[(g + 8) * NKT * 8 + 2 * tig] += acc[m][nt][2];
+          base[(g + 8) * NKT * 8 + 2 * tig + 1] += acc[m][nt][3];
+        }
+    }
+    __syncthreads();
+  }
+  float* row = ws + (size_t)blockIdx.x * ((size_t)CW * N);
+  for (int o = threadIdx.x; o < CW * N; o += 256) {
+    const int wc = o / N, n = o - wc * N;
+    row[o] = red[wc * NKT * 8 + n];
+  }
+}
+
 // mode 0: dw[(wc*Cn + nc)*taps + t]  (wide = output channels);  mode 1: dw[(nc*Cw + wc)*taps + t]; one warp per element
 __global__ void k_wgrad_narrow_reduce(const float* __restrict__ ws, int rows, int Cw, int taps, int Cn, int mode, float* __restrict__ dw,
                                       int accumulate) {
@@ -458,9 +697,40 @@ static int narrow_quad_launch(const void* x, int ldx, const void* w, const float
   return check_launch("conv_narrow_quad");
 }
 
+template <int CIN>
+static int first_mma_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cout,
+                            float* partials, int* nparts_host, cudaStream_t st) {
+  const long long ntiles = (long long)B * H * (W / 16);
+  long long g = (ntiles + 7) / 8;
+  if (g > 148 * 4) g = 148 * 4;
+  if (nparts_host) *nparts_host = (int)g;
+#define FM(NTV) k_conv_first_mma<CIN, NTV><<<(int)g, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)y, ldy, B, H, W, partials)
+  if (Cout == 64) FM(8);
+  else if (Cout == 32) FM(4);
+  else FM(2);
+#undef FM
+  return check_launch("conv_first_mma");
+}
+static int first_mma_mode() {      // USTRUN_FIRST_MMA=0 keeps the CUDA-core quad kernel (A/B comparisons)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USTRUN_FIRST_MMA");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 template <typename T>
 int narrow_in_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ks,
                      float* partials, int* nparts_host, cudaStream_t st) {
+  if (sizeof(T) == 2 && ks == 3 && W % 16 == 0 && Cin >= 1 && Cin <= 4 && (Cout == 64 || Cout == 32 || Cout == 16) && ldy % 8 == 0 && first_mma_mode() > 0) {
+    switch (Cin) {
+      case 1: return first_mma_launch<1>(x, ldx, w, bias, y, ldy, B, H, W, Cout, partials, nparts_host, st);
+      case 2: return first_mma_launch<2>(x, ldx, w, bias, y, ldy, B, H, W, Cout, partials, nparts_host, st);
+      case 3: return first_mma_launch<3>(x, ldx, w, bias, y, ldy, B, H, W, Cout, partials, nparts_host, st);
+      default: return first_mma_launch<4>(x, ldx, w, bias, y, ldy, B, H, W, Cout, partials, nparts_host, st);
+    }
+  }
   if (W % 4 == 0 && Cin >= 1 && Cin <= 4 && Cout <= 256 && ((size_t)ks * ks * Cin * Cout + 256 * 16) * sizeof(float) <= 48 * 1024) {
 #define NQ(CI, KSV) return narrow_quad_launch<T, CI, KSV>(x, ldx, w, bias, y, ldy, B, H, W, Cout, partials, nparts_host, st)
     if (ks == 3) { switch (Cin) { case 1: NQ(1, 3); case 2: NQ(2, 3); case 3: NQ(3, 3); default: NQ(4, 3); } }
@@ -492,25 +762,59 @@ int narrow_out_launch(const void* x, int ldx, const void* w, const float* bias, 
   k_conv_narrow_out<T><<<(int)g, 256, 0, st>>>((const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, y_nchw, B, H, W, Cin, Cout, ks);
   return check_launch("conv_narrow_out");
 }
+static int narrow_mma_mode() {      // USTRUN_NARROW_MMA=0 keeps the CUDA-core narrow weight-gradient kernel
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USTRUN_NARROW_MMA");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+template <int CN, int TAPS>
+static int narrow_wgrad_mma_launch(const void* wide, int ldw, int Cw, const void* nar, int ldn, int sgn, int B, int H, int W, float* ws, int grid,
+                                   cudaStream_t st) {
+#define NM(MTV) k_wgrad_narrow_mma<CN, TAPS, MTV><<<grid, 256, 0, st>>>((const __nv_bfloat16*)wide, ldw, (const __nv_bfloat16*)nar, ldn, sgn, B, H, W, ws)
+  if (Cw == 64) NM(4);
+  else if (Cw == 32) NM(2);
+  else NM(1);
+#undef NM
+  return check_launch("wgrad_narrow_mma");
+}
+
 template <typename T>
 int narrow_wgrad_launch(const void* wide, int ldw, int Cw, const void* nar, int ldn, int Cn, int ks, int sgn, int mode, int B, int H, int W,
                         float* dw, int accumulate, void* workspace, long long ws_bytes, cudaStream_t st) {
   long long M = (long long)B * H * W;
   const int TGv = narrow_tg(Cn, ks);
   const int per = (Cw / 8) * (ks * ks / TGv), lanes = 256 / per;
-  const int grid = narrow_wgrad_grid(M, lanes);
+  int grid = narrow_wgrad_grid(M, lanes);
   long long need = narrow_wgrad_ws_bytes(M, Cw, Cn, ks);
   if (!workspace || ws_bytes < need) { set_error("narrow wgrad: workspace too small (%lld < %lld)", ws_bytes, need); return USTRUN_ERR_ARG; }
+  const bool mma_ok = sizeof(T) == 2 && narrow_mma_mode() > 0 && W % 16 == 0 && ldw % 8 == 0 && (Cw == 64 || Cw == 32 || Cw == 16) && Cn >= 1 && Cn <= 4 &&
+                      (ks == 1 || ks == 3);
+  if (mma_ok) {
+    long long tiles = M / 16;
+    long long g = (tiles + 7) / 8;
+    if (g > grid) g = grid;                         // the workspace holds `grid` partial rows
+    grid = (int)(g < 1 ? 1 : g);
+    int rc;
+#define NMM(CNV) (ks == 3 ? narrow_wgrad_mma_launch<CNV, 9>(wide, ldw, Cw, nar, ldn, sgn, B, H, W, (float*)workspace, grid, st) \
+                          : narrow_wgrad_mma_launch<CNV, 1>(wide, ldw, Cw, nar, ldn, sgn, B, H, W, (float*)workspace, grid, st))
+    switch (Cn) { case 1: rc = NMM(1); break; case 2: rc = NMM(2); break; case 3: rc = NMM(3); break; default: rc = NMM(4); break; }
+#undef NMM
+    if (rc) return rc;
+  } else {
 #define NW_LAUNCH(CNV, TGV) k_wgrad_narrow<T, CNV, TGV><<<grid, 256, 0, st>>>((const T*)wide, ldw, Cw, (const T*)nar, ldn, ks, sgn, B, H, W, (float*)workspace)
-  if (ks == 1) {
-    switch (Cn) { case 1: NW_LAUNCH(1, 1); break; case 2: NW_LAUNCH(2, 1); break; case 3: NW_LAUNCH(3, 1); break; default: NW_LAUNCH(4, 1); break; }
-  } else if (Cn == 1) NW_LAUNCH(1, 9);
-  else if (Cn == 2) NW_LAUNCH(2, 3);
-  else if (Cn == 3) NW_LAUNCH(3, 3);
-  else NW_LAUNCH(4, 3);
+    if (ks == 1) {
+      switch (Cn) { case 1: NW_LAUNCH(1, 1); break; case 2: NW_LAUNCH(2, 1); break; case 3: NW_LAUNCH(3, 1); break; default: NW_LAUNCH(4, 1); break; }
+    } else if (Cn == 1) NW_LAUNCH(1, 9);
+    else if (Cn == 2) NW_LAUNCH(2, 3);
+    else if (Cn == 3) NW_LAUNCH(3, 3);
+    else NW_LAUNCH(4, 3);
 #undef NW_LAUNCH
-  int rc = check_launch("wgrad_narrow");
-  if (rc) return rc;
+    int rc = check_launch("wgrad_narrow");
+    if (rc) return rc;
+  }
   const int n = Cw * ks * ks * Cn;
   k_wgrad_narrow_reduce<<<(n + 7) / 8, 256, 0, st>>>((const float*)workspace, grid, Cw, ks * ks, Cn, mode, dw, accumulate);
   return check_launch("wgrad_narrow_reduce");

@@ -237,25 +237,32 @@ class PackedConv:
         self.key = None
         self.wf = None
         self.wd = None
+        self.has_wd = False
 
-    def get(self, weight: torch.Tensor, transposed=False):
+    def get(self, weight: torch.Tensor, transposed=False, need_wd=True):
+        """(wf, wd) for ``weight``.  ``need_wd=False`` (no-grad forwards: the teacher never runs a dgrad) packs only the
+        forward copy; the dgrad copy is added lazily the first time a caller asks for it."""
         tdt, code = _dt()
         key = (weight.data_ptr(), weight._version, code, getattr(weight, "_ustrun_epoch", 0))
-        if key != self.key:
+        fresh = key != self.key
+        if fresh or (need_wd and not self.has_wd):
             w = weight.detach()
             if w.dtype != torch.float32 or not w.is_contiguous():
                 w = w.float().contiguous()
             if transposed:
                 cin, cout = w.shape[0], w.shape[1]
-                self.wf = torch.empty((4, cout, cin), dtype=tdt, device=w.device)
-                self.wd = torch.empty((cin, 4, cout), dtype=tdt, device=w.device)
-                _call("ustrun_pack_convT_weight", _ptr(w), _ptr(self.wf), _ptr(self.wd), code, cin, cout, _stream())
+                if fresh:
+                    self.wf = torch.empty((4, cout, cin), dtype=tdt, device=w.device)
+                self.wd = torch.empty((cin, 4, cout), dtype=tdt, device=w.device) if need_wd else None
+                _call("ustrun_pack_convT_weight", _ptr(w), _ptr(self.wf) if fresh else None, _ptr(self.wd), code, cin, cout, _stream())
             else:
                 cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
-                self.wf = torch.empty((cout, k * k, cin), dtype=tdt, device=w.device)
-                self.wd = torch.empty((cin, k * k, cout), dtype=tdt, device=w.device)
-                _call("ustrun_pack_conv_weight", _ptr(w), _ptr(self.wf), _ptr(self.wd), code, cout, cin, k, _stream())
+                if fresh:
+                    self.wf = torch.empty((cout, k * k, cin), dtype=tdt, device=w.device)
+                self.wd = torch.empty((cin, k * k, cout), dtype=tdt, device=w.device) if need_wd else None
+                _call("ustrun_pack_conv_weight", _ptr(w), _ptr(self.wf) if fresh else None, _ptr(self.wd), code, cout, cin, k, _stream())
             self.key = key
+            self.has_wd = need_wd
         return self.wf, self.wd
 
 
@@ -336,7 +343,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
     Reference: unet_parts.py:15-21,34 / unet.py:52-72,96-117."""
     ks = conv.kernel_size[0]
     cout = conv.out_channels
-    wf, wd = packed.get(conv.weight)
+    wf, wd = packed.get(conv.weight, need_wd=ctx.need_grad)
     dev = x.t.device
     raw = x.like(cout)
     training = ctx.training and bn.training if hasattr(bn, "training") else ctx.training
@@ -439,7 +446,7 @@ def _assign_grad(x: Act, gx: Act):
 def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
     """nn.ConvTranspose2d(k2, s2) + bias, written straight into ``out`` (usually the second half
     of the decoder's concat buffer): unet_parts.py:53,57,62-67."""
-    wf, wd = packed.get(up.weight, transposed=True)
+    wf, wd = packed.get(up.weight, transposed=True, need_wd=ctx.need_grad)
     cin, cout = up.in_channels, up.out_channels
     impl = _impl_for(cin, cout, x.dtype_code)
     _call("ustrun_convT2x2_fwd", impl, x.ptr, x.ld, _ptr(wf), _ptr(up.bias), out.ptr, out.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream())
@@ -494,7 +501,7 @@ def head_conv(ctx: Ctx, x: Act, conv, packed: PackedConv):
     Returns (logits, backward_fn(dlogits, sink))."""
     ks = conv.kernel_size[0]
     cout = conv.out_channels
-    wf, wd = packed.get(conv.weight)
+    wf, wd = packed.get(conv.weight, need_wd=ctx.need_grad)
     logits = torch.empty((x.B, cout, x.H, x.W), dtype=torch.float32, device=x.t.device)
     _raw_conv(x, wf, conv.bias, None, ks, out_nchw=logits)
 
