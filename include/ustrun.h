@@ -210,6 +210,16 @@ long long ustrun_fft_amp_mix_workspace_bytes(int N, int C, int H, int W, double 
 int ustrun_fft_amp_mix(const float* src, const float* trg, const double* ratio, double L, float* out, int N, int C, int H, int W,
                        void* workspace, long long ws_bytes, void* stream);
 
+/* ---- hardness of the unlabelled samples -----------------------------------
+ * Replaces train.py:705-718 (stu_pseudo_label.cpu() / pseudo_label.cpu() -> utils/metrics.py dice_coeff :149-174,
+ * dice_coeff_2label :176-201, dice_coeff_3label :203-231 -> dice_coefficient_numpy :114-146): per sample
+ * dice_p = (2I+1)/(1.001+S+G) (0 if S = G = 0) over `parts`, hardness[b] = 1 - mean_p dice_p (1 in the first epoch),
+ * lq_idx = first argmax.  stu_pl / tea_pl: uint8 label planes from ustrun_pseudo_label_* ([B,H,W]; mode 1: [B,2,H,W]).
+ * mode 0: label != 0 (prostate, BUSI); 1: two sigmoid channels (fundus); 2: classes 1..3 (M&Ms).
+ * workspace: unsigned int[B*3*3]; hardness: double[B]; dice: double[parts][B] or NULL; lq_idx: int[1]. */
+int ustrun_hardness(const unsigned char* stu_pl, const unsigned char* tea_pl, int B, int H, int W, int mode, int first_epoch,
+                    unsigned int* workspace, double* hardness, double* dice, int* lq_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

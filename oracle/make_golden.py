@@ -310,13 +310,47 @@ def case_fft_mix():
     print("fft_mix: reference == oracle bit-for-bit on", len(fx) // 5, "cases")
 
 
+def case_hardness():
+    """train.py:705-718 with the reference's own utils/metrics.py functions vs the oracle restatement."""
+    from oracle import hardness_ref as Hr
+    from utils import metrics as ref_metrics               # reference
+    rng = np.random.RandomState(SEED)
+    fx = {}
+    for tag, mode, fn, shape, hi in (("binary", "binary", ref_metrics.dice_coeff, (5, 24, 24), 2), ("2label", "2label", ref_metrics.dice_coeff_2label, (4, 2, 24, 24), 2),
+                                     ("3label", "3label", ref_metrics.dice_coeff_3label, (4, 24, 24), 4)):
+        stu = rng.randint(0, hi, shape).astype(np.int64)
+        tea = np.where(rng.rand(*shape) < 0.8, stu, rng.randint(0, hi, shape)).astype(np.int64)
+        stu[0] = 0                                          # a sample whose student map is empty ...
+        tea[0] = 0                                          # ... and whose teacher map is empty too (dice := 0)
+        tea[1] = 0
+        arrs = fn(np.asarray(torch.from_numpy(stu).clone().cpu()), torch.from_numpy(tea).clone().cpu(), ret_arr=True)   # train.py:705
+        n_part = len(arrs)
+        tmp = arrs[0]
+        for i in range(1, n_part):                           # train.py:706-710
+            tmp += arrs[i]
+        ref_h = 1 - tmp / n_part
+        lq_idx, max_v = 0, -1
+        for i in range(len(ref_h)):                          # train.py:714-718
+            if ref_h[i] > max_v:
+                max_v, lq_idx = ref_h[i], i
+        h, lq, _ = Hr.hardness(stu, tea, mode)
+        assert np.array_equal(h, ref_h) and lq == lq_idx, f"hardness oracle differs from the reference ({tag})"
+        fx[f"{tag}/stu"], fx[f"{tag}/tea"], fx[f"{tag}/hardness"], fx[f"{tag}/lq_idx"] = stu.astype(np.uint8), tea.astype(np.uint8), ref_h, np.asarray(lq_idx)
+    np.savez_compressed(os.path.join(OUT, "hardness.npz"), **fx)
+    print("hardness: reference == oracle bit-for-bit on 3 modes")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     if len(sys.argv) > 1 and sys.argv[1] == "fft":
         case_fft_mix()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "hardness":
+        case_hardness()
+        return
     case_fft_mix()
+    case_hardness()
     case_losses()
     case_unet_a(1, 2, 32, 2)
     case_unet_a(3, 3, 32, 2)

@@ -159,3 +159,15 @@ def test_fft_mix_oracle_reproduces_reference_fixture():
         assert got.dtype == np.float32
         # bit-for-bit in the build container; another BLAS/pocketfft build may differ in the last float64 bit
         assert np.allclose(got, fx[f"{tag}/out"], rtol=0, atol=2e-6), tag
+
+
+def test_hardness_oracle_reproduces_reference_fixture():
+    """oracle/hardness_ref.py against tests/golden/hardness.npz (outputs of the reference's utils/metrics.py
+    dice_coeff / dice_coeff_2label / dice_coeff_3label through the train.py:705-718 bookkeeping)."""
+    from oracle import hardness_ref as Hr
+    fx = np.load(os.path.join(GOLDEN, "hardness.npz"))
+    for mode in ("binary", "2label", "3label"):
+        h, lq, _ = Hr.hardness(fx[f"{mode}/stu"], fx[f"{mode}/tea"], mode)
+        assert np.array_equal(h, fx[f"{mode}/hardness"]) and lq == int(fx[f"{mode}/lq_idx"]), mode
+        h1, lq1, _ = Hr.hardness(fx[f"{mode}/stu"], fx[f"{mode}/tea"], mode, first_epoch=True)
+        assert np.all(h1 == 1) and lq1 == 0

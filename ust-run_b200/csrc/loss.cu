@@ -370,6 +370,62 @@ static inline int loss_grid(long long n) {
   return (int)(b < 1 ? 1 : b);
 }
 
+// ------------------------------------------------------------------------------------------
+// hardness of the unlabelled samples (train.py:705-718, utils/metrics.py:114-231)
+// ------------------------------------------------------------------------------------------
+// Per sample and part: S = #student, G = #teacher, I = #both (booleans), exactly what dice_coefficient_numpy counts
+// after its .cpu() copies.  mode 0: one part, label != 0 (dice_coeff: prostate / BUSI); mode 1: planes [B][2][HW], one
+// part per channel (dice_coeff_2label: fundus); mode 2: parts = classes 1..3 of one label plane (dice_coeff_3label: M&Ms).
+__global__ void __launch_bounds__(256)
+k_hardness_counts(const uint8_t* __restrict__ stu, const uint8_t* __restrict__ tea, int HW, int mode, int parts, unsigned int* __restrict__ counts) {
+  const int b = blockIdx.x, part = blockIdx.y;
+  const long long plane = mode == 1 ? ((long long)b * parts + part) * HW : (long long)b * HW;
+  const uint8_t* ps = stu + plane;
+  const uint8_t* pt = tea + plane;
+  const int cls = part + 1;
+  unsigned int S = 0, G = 0, I = 0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const bool s_ = mode == 2 ? ps[i] == cls : ps[i] != 0;
+    const bool g_ = mode == 2 ? pt[i] == cls : pt[i] != 0;
+    S += s_; G += g_; I += (s_ && g_);
+  }
+  __shared__ unsigned int sm[3][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    S += __shfl_xor_sync(0xffffffffu, S, o); G += __shfl_xor_sync(0xffffffffu, G, o); I += __shfl_xor_sync(0xffffffffu, I, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = S; sm[1][threadIdx.x >> 5] = G; sm[2][threadIdx.x >> 5] = I; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    unsigned int t = 0;
+    for (int w = 0; w < 8; ++w) t += sm[threadIdx.x][w];
+    counts[((size_t)b * parts + part) * 3 + threadIdx.x] = t;
+  }
+}
+// dice = (2I + 1) / (1.001 + S + G), 0 when both are empty (metrics.py:139-143); hardness = 1 - mean over parts
+// (train.py:706-710), all ones in the first epoch (:711-713); lq_idx = first maximum (:714-718).  float64 like Python.
+__global__ void k_hardness_finalize(const unsigned int* __restrict__ counts, int B, int parts, int first_epoch, double* __restrict__ hardness,
+                                    double* __restrict__ dice_out, int* __restrict__ lq_idx) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int best = 0;
+  double maxv = -1.0;
+  for (int b = 0; b < B; ++b) {
+    double tmp = 0.0;
+    for (int p = 0; p < parts; ++p) {
+      const unsigned int* c = counts + ((size_t)b * parts + p) * 3;
+      const double S = (double)c[0], G = (double)c[1], I = (double)c[2];
+      const double d = (c[0] == 0 && c[1] == 0) ? 0.0 : (2.0 * I + 1.0) / (1.001 + S + G);
+      if (dice_out) dice_out[(size_t)p * B + b] = d;
+      tmp = p == 0 ? d : tmp + d;
+    }
+    double h = 1.0 - tmp / (double)parts;
+    if (first_epoch) h = 1.0;
+    hardness[b] = h;
+    if (h > maxv) { maxv = h; best = b; }
+  }
+  *lq_idx = best;
+}
+
 }  // namespace ustrun
 
 using namespace ustrun;
@@ -502,6 +558,15 @@ int ustrun_bce_dice_sigmoid_bwd(const float* logits, const uint8_t* target, cons
   if (grid > 148 * 8) grid = 148 * 8;
   k_bce_dice_pass2<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, mask, n, coef, upstream, gscale, dlogits, accumulate);
   return check_launch("bce_dice_sigmoid_bwd");
+}
+
+int ustrun_hardness(const uint8_t* stu_pl, const uint8_t* tea_pl, int B, int H, int W, int mode, int first_epoch, unsigned int* workspace,
+                    double* hardness, double* dice, int* lq_idx, void* stream) {
+  USTRUN_REQUIRE(stu_pl && tea_pl && workspace && hardness && lq_idx && B > 0 && H > 0 && W > 0 && mode >= 0 && mode <= 2, "hardness: bad args");
+  const int parts = mode == 0 ? 1 : (mode == 1 ? 2 : 3);
+  k_hardness_counts<<<dim3(B, parts), 256, 0, (cudaStream_t)stream>>>(stu_pl, tea_pl, H * W, mode, parts, workspace);
+  k_hardness_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, B, parts, first_epoch, hardness, dice, lq_idx);
+  return check_launch("hardness");
 }
 
 }  // extern "C"

@@ -222,11 +222,14 @@ class Ctx:
         self.bn_world = 1
         self.bn_peer = getattr(bn_sync, "peer", None)   # PeerStats: fused finalize + NVLink peer-memory reduction
 
-    def backward(self, sink: GradSink):
+    def backward(self, sink: GradSink, join: bool = True):
+        """``join=False`` leaves the weight-gradient side stream running (the fused step joins once, before the
+        optimiser, so the tail of one branch's weight gradients overlaps the next branch's forward)."""
         for fn in reversed(self.tape):
             fn(sink)
         self.tape = []
-        join_side_stream()               # weight gradients are complete for whoever runs next on this stream
+        if join:
+            join_side_stream()           # weight gradients are complete for whoever runs next on this stream
 
 
 # --------------------------------------------------------------------------------------------

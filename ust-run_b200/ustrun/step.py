@@ -89,13 +89,16 @@ def mix_input(a, b, box_u8, b_index=None) -> E.Act:
 class SSLTrainer:
     def __init__(self, model, ema_model, n_classes, branch="softmax", base_lr=0.03, max_iterations=30000, threshold=0.95,
                  consistency=1.0, consistency_rampup=200.0, ema_decay=0.99, momentum=0.9, weight_decay=1e-4, dp=None,
-                 forward_kwargs=None, fft_window=0.01):
+                 forward_kwargs=None, fft_window=0.01, hardness_mode=None):
         self.model, self.ema_model = model, ema_model
         self.n_classes, self.branch = n_classes, branch
         self.base_lr, self.lr, self.max_iterations = base_lr, base_lr, max_iterations
         self.threshold, self.consistency, self.consistency_rampup, self.ema_decay = threshold, consistency, consistency_rampup, ema_decay
         self.iter_num = 0
         self.fft_window = fft_window          # --LB (train.py:76): half-width of the amplitude window as a fraction of min(H, W)
+        # "binary" | "2label" | "3label": also return the per-sample hardness / hardest-sample index (train.py:705-718)
+        self.hardness_mode = hardness_mode
+        self.first_epoch = False              # train.py:711-713: hardness is 1 for every sample during epoch 0
         self.dp = dp
         self.forward_kwargs = forward_kwargs or {}
         self.params = list(model.parameters())
@@ -191,7 +194,37 @@ class SSLTrainer:
         self.iter_num = it + 1
         loss = l_sup[0] + cw * (l_ul[0] + l_lu[0] + cw * l_s[0])
         out = dict(comp)
+        if self.hardness_mode is not None:
+            out["hardness"], out["lq_idx"], out["stu_tea_dice"] = hardness(comp["stu_pseudo_label"], comp["pseudo_label"], self.hardness_mode, self.first_epoch)
         out.update(loss=loss, sup_loss=l_sup[0], unsup_loss_ul=l_ul[0], unsup_loss_lu=l_lu[0], unsup_loss_s=l_s[0], consistency_weight=cw)
         if keep_logits:
             out["logits"] = dict(t1=t1, t2=t2, t3=t3, s0=s0, lb=lg_lb, ul=lg_ul, lu=lg_lu, s=lg_s)
         return out
+
+
+HARDNESS_MODES = {"binary": 0, "2label": 1, "3label": 2}
+
+
+def hardness(stu_pseudo_label: torch.Tensor, pseudo_label: torch.Tensor, mode: str = "binary", first_epoch: bool = False):
+    """Per-sample hardness of the unlabelled batch on the device (train.py:705-718): ``1 - Dice(student pseudo label,
+    teacher pseudo label)`` with the reference's ``dice_coefficient_numpy`` formula (utils/metrics.py:114-146), averaged
+    over the dataset's label parts, plus the index of the hardest ("low quality") sample.  ``mode``: "binary"
+    (metrics.dice_coeff: prostate / BUSI), "2label" (dice_coeff_2label: fundus, planes [B,2,H,W]), "3label"
+    (dice_coeff_3label: M&Ms).  Returns (hardness float64 [B], lq_idx int32 [1], dice float64 [parts,B]) -- device
+    tensors, no host synchronisation (the reference copies both label maps to the host here)."""
+    L.require_device()
+    m = HARDNESS_MODES[mode]
+    s, t = as_u8(stu_pseudo_label).contiguous(), as_u8(pseudo_label).contiguous()
+    if s.shape != t.shape or s.dim() != (4 if m == 1 else 3):
+        raise ValueError("hardness: label planes must have the same shape ([B,H,W]; [B,2,H,W] for '2label')")
+    if m == 1 and s.shape[1] != 2:
+        raise ValueError("hardness: '2label' expects two channels")
+    B, H, W = s.shape[0], s.shape[-2], s.shape[-1]
+    parts = (1, 2, 3)[m]
+    dev = s.device
+    ws = torch.empty(B * 9, dtype=torch.int32, device=dev)
+    hard = torch.empty(B, dtype=torch.float64, device=dev)
+    dice = torch.empty((parts, B), dtype=torch.float64, device=dev)
+    lq = torch.empty(1, dtype=torch.int32, device=dev)
+    _call("ustrun_hardness", _ptr(s), _ptr(t), B, H, W, m, 1 if first_epoch else 0, _ptr(ws), _ptr(hard), _ptr(dice), _ptr(lq), _stream())
+    return hard, lq, dice
