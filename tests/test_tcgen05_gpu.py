@@ -122,3 +122,44 @@ def test_tc_matches_simt_bitwise_inputs():
     E.set_force_simt(False)
     d = (y1.t.float() - y2.t.float()).abs().max()
     assert float(d) <= 2 ** -6 * float(y2.t.float().abs().max())
+
+
+MID_SHAPES = [  # B, Cin, Cout, H, W: the 16/32-channel levels of UNet-B (warp-level MMA kernels, csrc/mid_conv.cu)
+    (2, 16, 16, 12, 48), (1, 16, 32, 9, 64), (2, 32, 32, 8, 32), (1, 32, 64, 6, 48), (1, 64, 32, 5, 80), (2, 32, 16, 7, 16),
+    (1, 16, 16, 4, 384),
+]
+
+
+@pytest.mark.parametrize("B,cin,cout,H,W", MID_SHAPES)
+@pytest.mark.parametrize("ks", [3, 1])
+def test_mid_mma_conv_fwd_stats_dgrad_wgrad(B, cin, cout, H, W, ks):
+    from ustrun import _lib as L
+    E = _setup()
+    torch.manual_seed(B * 100 + cin + cout + H + ks)
+    x = torch.randn(B, cin, H, W, device="cuda")
+    w = torch.randn(cout, cin, ks, ks, device="cuda") * (1.0 / (cin * ks * ks) ** 0.5)
+    a = E.input_nchw(x)
+    wf, wd = E.PackedConv().get(w)
+    xr, wr = x.bfloat16().float(), w.bfloat16().float()
+    ref = F.conv2d(xr, wr, padding=ks // 2)
+    y = a.like(cout)
+    part = torch.zeros(L.MAX_PARTS * 2 * cout, device="cuda")
+    assert E._impl_for(cin, cout, L.BF16) == L.SIMT          # dispatched inside the C ABI to the mid-channel MMA kernels
+    nparts = E._raw_conv(a, wf, None, y, ks, part)
+    got = E.to_nchw(y)
+    assert rel_err(got, ref) < 5e-3, "mid conv forward"
+    sums = part[: nparts * 2 * cout].view(nparts, 2, cout).sum(0)
+    assert rel_err(sums[0], ref.sum((0, 2, 3))) < 2e-3 and rel_err(sums[1], (ref * ref).sum((0, 2, 3))) < 2e-3, "fused BN statistics"
+    dy = torch.randn_like(ref)
+    g = E.input_nchw(dy)
+    dyr = dy.bfloat16().float()
+    gx = a.like(cin)
+    E._raw_conv(g, wd, None, gx, ks)
+    ref_dx = torch.autograd.grad(F.conv2d(xr.requires_grad_(), wr, padding=ks // 2), xr, dyr)[0]
+    assert rel_err(E.to_nchw(gx), ref_dx) < 5e-3, "mid conv dgrad"
+    dw = torch.zeros_like(w)
+    E._wgrad(g, a, dw, 0, ks)
+    ref_dw = torch.autograd.grad(F.conv2d(xr.detach(), wr.requires_grad_(), padding=ks // 2), wr, dyr)[0]
+    assert rel_err(dw, ref_dw) < 2e-3, "mid conv wgrad"
+    E._wgrad(g, a, dw, 1, ks)
+    assert rel_err(dw, 2 * ref_dw) < 2e-3

@@ -25,6 +25,14 @@ template <typename T>
 int narrow_wgrad_launch(const void* wide, int ldw, int Cw, const void* nar, int ldn, int Cn, int ks, int sgn, int mode, int B, int H, int W,
                         float* dw, int accumulate, void* workspace, long long ws_bytes, cudaStream_t st);
 
+bool mid_conv_ok(int Cin, int Cout, int ks, int W, int ldx, int ldy);
+bool mid_wgrad_ok(int Cin, int Cout, int ks, int ldx, int lddy);
+long long mid_wgrad_ws_bytes(int Cin, int Cout, int ks);
+int mid_conv_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ks,
+                    float* partials, int* nparts_host, cudaStream_t st);
+int mid_wgrad_launch(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout, int ks,
+                     void* workspace, long long ws_bytes, cudaStream_t st);
+
 int tc_conv_fwd(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize,
                 float* partials, int* nparts_host, cudaStream_t st);
 int tc_convT_fwd(const void* x, int ldx, const void* wf, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
@@ -66,6 +74,8 @@ int ustrun_conv_fwd(int impl, const void* x, int ldx, const void* w_packed, cons
     if (dtype == USTRUN_F32) return narrow_out_launch<float>(x, ldx, w_packed, bias, y, ldy, ynchw, B, H, W, Cin, Cout, ksize, st);
     return narrow_out_launch<__nv_bfloat16>(x, ldx, w_packed, bias, y, ldy, ynchw, B, H, W, Cin, Cout, ksize, st);
   }
+  if (dtype == USTRUN_BF16 && !out_nchw_f32 && mid_conv_ok(Cin, Cout, ksize, W, ldx, ldy))       // UNet-B 16/32-channel levels: warp-level MMA
+    return mid_conv_launch(x, ldx, w_packed, bias, y, ldy, B, H, W, Cin, Cout, ksize, partials, nparts_host, st);
   ConvGeom g{B, H, W, Cin, Cout, ksize, 0, -1};
   if (dtype == USTRUN_F32) return simt_conv_launch<float>(x, ldx, w_packed, bias, y, ldy, ynchw, g, partials, nparts_host, st);
   return simt_conv_launch<__nv_bfloat16>(x, ldx, w_packed, bias, y, ldy, ynchw, g, partials, nparts_host, st);
@@ -78,6 +88,10 @@ long long ustrun_conv_wgrad_workspace_bytes(int impl, int B, int H, int W, int C
   long long generic = simt_wgrad_ws_bytes((long long)B * H * W, Cout, Cin, ksize * ksize), narrow = 0;
   if (Cin <= 8 && narrow_wgrad_ok(Cout, Cin, ksize)) narrow = narrow_wgrad_ws_bytes((long long)B * H * W, Cout, Cin, ksize);
   else if (Cout <= 8 && narrow_wgrad_ok(Cin, Cout, ksize)) narrow = narrow_wgrad_ws_bytes((long long)B * H * W, Cin, Cout, ksize);
+  if (mid_wgrad_ok(Cin, Cout, ksize, 8, 8)) {
+    const long long mid = mid_wgrad_ws_bytes(Cin, Cout, ksize);
+    if (mid > narrow) narrow = mid;
+  }
   return generic > narrow ? generic : narrow;
 }
 
@@ -95,6 +109,8 @@ int ustrun_conv_wgrad(int impl, const void* dy, int lddy, const void* x, int ldx
     if (dtype == USTRUN_F32) return narrow_wgrad_launch<float>(x, ldx, Cin, dy, lddy, Cout, ksize, -1, 1, B, H, W, dw, accumulate, workspace, workspace_bytes, st);
     return narrow_wgrad_launch<__nv_bfloat16>(x, ldx, Cin, dy, lddy, Cout, ksize, -1, 1, B, H, W, dw, accumulate, workspace, workspace_bytes, st);
   }
+  if (dtype == USTRUN_BF16 && mid_wgrad_ok(Cin, Cout, ksize, ldx, lddy))
+    return mid_wgrad_launch(dy, lddy, x, ldx, dw, accumulate, B, H, W, Cin, Cout, ksize, workspace, workspace_bytes, st);
   ConvGeom g{B, H, W, Cin, Cout, ksize, 0, -1};
   if (dtype == USTRUN_F32) return simt_wgrad_launch<float>(dy, lddy, x, ldx, dw, accumulate, g, Cout, Cin, workspace, workspace_bytes, st);
   return simt_wgrad_launch<__nv_bfloat16>(dy, lddy, x, ldx, dw, accumulate, g, Cout, Cin, workspace, workspace_bytes, st);

@@ -94,8 +94,11 @@ def last_error() -> str:
     return (lib.ustrun_last_error_string() or b"").decode()
 
 
+_FN = {_name: getattr(lib, _name) for _name in _SIGS}        # bound once: the step makes ~1300 calls
+
+
 def call(name: str, *args) -> None:
-    rc = getattr(lib, name)(*args)
+    rc = _FN[name](*args)
     if rc != 0:
         raise UstrunError(f"{name} failed (code {rc}): {last_error()}")
 
