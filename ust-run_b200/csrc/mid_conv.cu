@@ -37,23 +37,49 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const void* smem
 // ------------------------------------------------------------------------------------------
 // forward / dgrad
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+// A warp owns 16 consecutive pixels of an image row.  Per tile: the KS x (16 + 2R)-pixel input neighbourhood is staged
+// in a warp-private shared slab with 16-byte loads (prefetched into registers one tile ahead, zero padded), every
+// 16-channel K step is ONE ldmatrix.x4 (row-shifted by the tap) instead of four predicated global loads, and the
+// weights are kept in shared memory in B-fragment order so that one LDS.128 per lane feeds two n-tiles.
 template <int CIN, int NT, int KS>          // NT = Cout / 8, KS = 1 | 3
+struct MidCfg {
+  static constexpr int R = KS >> 1, TAPS = KS * KS, K = TAPS * CIN, KSTEPS = K / 16, COUT = NT * 8, CPT = CIN / 16;
+  static constexpr int XW = 16 + 2 * R, XP = CIN + 8, SP = COUT + 8;
+  static constexpr int slab_elems = KS * XW * XP, stg_elems = 16 * SP;
+  static constexpr int warp_elems = ((slab_elems > stg_elems ? slab_elems : stg_elems) + 7) / 8 * 8;   // bf16 per warp, 16-byte multiple
+  static constexpr int wfrag_u32 = KSTEPS * (NT / 2) * 32 * 4;                                          // [s][j2][lane][4]
+  static constexpr int NCH = (KS * XW * (CIN / 8) + 31) / 32;                                           // 16-byte slab chunks per lane
+  static constexpr size_t smem = (size_t)wfrag_u32 * 4 + (size_t)8 * warp_elems * 2 + (size_t)8 * 2 * COUT * 4;
+};
+
+template <int CIN, int NT, int KS>
 __global__ void __launch_bounds__(256)
 k_conv_mid_mma(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias,
                __nv_bfloat16* __restrict__ y, int ldy, int B, int H, int W, float* __restrict__ partials) {
-  constexpr int TAPS = KS * KS, K = TAPS * CIN, KSTEPS = K / 16, COUT = NT * 8, WP = K + 8, SP = COUT + 8, CPT = CIN / 16;
+  using Cfg = MidCfg<CIN, NT, KS>;
+  constexpr int R = Cfg::R, TAPS = Cfg::TAPS, K = Cfg::K, KSTEPS = Cfg::KSTEPS, COUT = Cfg::COUT, CPT = Cfg::CPT;
+  constexpr int XW = Cfg::XW, XP = Cfg::XP, SP = Cfg::SP, NCH = Cfg::NCH;
   extern __shared__ __align__(16) uint8_t mid_smem[];
-  __nv_bfloat16* w_s = reinterpret_cast<__nv_bfloat16*>(mid_smem);                 // [COUT][WP]
-  __nv_bfloat16* stg_all = w_s + COUT * WP;                                         // [8 warps][16][SP]
-  float* red = reinterpret_cast<float*>(stg_all + 8 * 16 * SP);                     // [8][2*COUT]
-  for (int i = threadIdx.x; i < COUT * (K / 8); i += 256) {                         // 16-byte chunks of the packed weights
-    const int co = i / (K / 8), c = i - co * (K / 8);
-    *reinterpret_cast<uint4*>(w_s + co * WP + c * 8) = *reinterpret_cast<const uint4*>(wp + (size_t)co * K + c * 8);
+  uint32_t* wfrag = reinterpret_cast<uint32_t*>(mid_smem);                                   // B fragments, [s][j2][lane][4]
+  __nv_bfloat16* warp_all = reinterpret_cast<__nv_bfloat16*>(wfrag + Cfg::wfrag_u32);        // [8 warps][warp_elems]
+  float* red = reinterpret_cast<float*>(warp_all + 8 * Cfg::warp_elems);                     // [8][2*COUT]
+  // weights -> fragment order: entry (s, j, lane) = { w[co][16s + 2tig, +1], w[co][16s + 8 + 2tig, +1] }, co = 8j + g
+  for (int i = threadIdx.x; i < KSTEPS * NT * 32; i += 256) {
+    const int ln = i & 31, j = (i >> 5) % NT, s_ = i / (32 * NT);
+    const uint32_t* wr = reinterpret_cast<const uint32_t*>(wp + (size_t)(8 * j + (ln >> 2)) * K + 16 * s_ + 2 * (ln & 3));
+    uint32_t* d = wfrag + ((s_ * (NT / 2) + (j >> 1)) * 32 + ln) * 4 + 2 * (j & 1);
+    d[0] = wr[0];
+    d[1] = wr[4];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int g = lane >> 2, tig = lane & 3;
-  __nv_bfloat16* st = stg_all + wrp * 16 * SP;
+  __nv_bfloat16* slab = warp_all + wrp * Cfg::warp_elems;       // [KS][XW][XP]; reused as the [16][SP] output staging tile
   float bs[NT][2], ssum[NT][2], ssq[NT][2];
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
@@ -61,39 +87,63 @@ k_conv_mid_mma(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16
     ssum[j][0] = ssum[j][1] = ssq[j][0] = ssq[j][1] = 0.f;
   }
   const int tiles_w = W >> 4;
-  const long long ntiles = (long long)B * H * tiles_w;
-  for (long long tl = (long long)blockIdx.x * 8 + wrp; tl < ntiles; tl += (long long)gridDim.x * 8) {
+  const long long ntiles = (long long)B * H * tiles_w, tstep = (long long)gridDim.x * 8;
+  uint4 pre[NCH];
+  auto load_slab = [&](long long tile) {       // global -> registers, zero padding; chunk c = (row r, pixel p, 8-channel group q)
+    int tw, h_, b_;
+    pix_decomp(tile, tiles_w, H, b_, h_, tw);
+    const int w0 = tw << 4;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      pre[i] = make_uint4(0, 0, 0, 0);
+      if (c < KS * XW * (CIN / 8)) {
+        const int q = c % (CIN / 8), p = (c / (CIN / 8)) % XW, r = c / ((CIN / 8) * XW);
+        const int hh = h_ + r - R, ww = w0 + p - R;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) pre[i] = *reinterpret_cast<const uint4*>(x + ((long long)(b_ * H + hh) * W + ww) * ldx + q * 8);
+      }
+    }
+  };
+  long long tl = (long long)blockIdx.x * 8 + wrp;
+  if (tl < ntiles) load_slab(tl);
+  const int mat = lane >> 3, rr = lane & 7;
+  for (; tl < ntiles; tl += tstep) {
     int tw, h_, b_;
     pix_decomp(tl, tiles_w, H, b_, h_, tw);
     const int w0 = tw << 4;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < KS * XW * (CIN / 8)) {
+        const int q = c % (CIN / 8), p = (c / (CIN / 8)) % XW, r = c / ((CIN / 8) * XW);
+        *reinterpret_cast<uint4*>(slab + (r * XW + p) * XP + q * 8) = pre[i];
+      }
+    }
+    __syncwarp();
+    if (tl + tstep < ntiles) load_slab(tl + tstep);
     float acc[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) {
-      const int dy = KS == 3 ? t / 3 - 1 : 0, dx = KS == 3 ? t % 3 - 1 : 0;
-      const int hh = h_ + dy;
-      const bool rowok = hh >= 0 && hh < H;
-      const int wa = w0 + g + dx, wb = wa + 8;                   // pixel columns of fragment rows g and g + 8
-      const bool oka = rowok && wa >= 0 && wa < W, okb = rowok && wb >= 0 && wb < W;
-      const __nv_bfloat16* rowp = x + ((long long)(b_ * H + (rowok ? hh : h_)) * W) * ldx + 2 * tig;
-      const uint32_t* pa = reinterpret_cast<const uint32_t*>(rowp + (long long)(oka ? wa : w0) * ldx);
-      const uint32_t* pb = reinterpret_cast<const uint32_t*>(rowp + (long long)(okb ? wb : w0) * ldx);
+      const int dyi = KS == 3 ? t / 3 : 0, dxi = KS == 3 ? t % 3 : 0;
+      // A fragment rows = pixels (slab column p + dxi), matrices: (pixels 0-7 | 8-15) x (channels +0 | +8)
+      const __nv_bfloat16* arow = slab + (dyi * XW + dxi + rr + 8 * (mat & 1)) * XP + 8 * (mat >> 1);
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {                            // 16-channel K steps of this tap
+      for (int c = 0; c < CPT; ++c) {
         uint32_t af[4];
-        af[0] = oka ? pa[8 * c] : 0u;                             // channels 16c + 2tig, +1     (uint32 index: 16c/2)
-        af[1] = okb ? pb[8 * c] : 0u;
-        af[2] = oka ? pa[8 * c + 4] : 0u;                         // channels 16c + 8 + 2tig, +1
-        af[3] = okb ? pb[8 * c + 4] : 0u;
+        ldsm_x4(af, arow + 16 * c);
         const int s_ = t * CPT + c;
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const uint32_t* wr = reinterpret_cast<const uint32_t*>(w_s + (8 * j + g) * WP + 16 * s_ + 2 * tig);
-          mma16816(acc[j], af, wr[0], wr[4]);
+        for (int j2 = 0; j2 < NT / 2; ++j2) {
+          const uint4 bq = *reinterpret_cast<const uint4*>(wfrag + ((s_ * (NT / 2) + j2) * 32 + lane) * 4);
+          mma16816(acc[2 * j2], af, bq.x, bq.y);
+          mma16816(acc[2 * j2 + 1], af, bq.z, bq.w);
         }
       }
     }
+    __syncwarp();                                // every lane is done with the slab: reuse it as the output staging tile
+    __nv_bfloat16* st = slab;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       ssum[j][0] += acc[j][0] + acc[j][2]; ssum[j][1] += acc[j][1] + acc[j][3];
@@ -152,24 +202,46 @@ k_wgrad_mid_mma(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloa
     for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
   const int segs_w = (W + 63) >> 6;
   const long long nsegs = (long long)B * H * segs_w;
-  const uint4 z4 = make_uint4(0, 0, 0, 0);
-  for (long long sg = blockIdx.x; sg < nsegs; sg += gridDim.x) {
+  // 16-byte chunks of a run: first the dY run [64][COUT/8], then the X neighbourhood [XR][XW][CIN/8]; every thread
+  // prefetches its chunks of the NEXT run into registers while the current one is consumed from shared memory
+  constexpr int NY = 64 * (COUT / 8), NX = XR * XW * (CIN / 8), NCH = (NY + NX + NTHR - 1) / NTHR;
+  uint4 pre[NCH];
+  auto load_run = [&](long long seg) {
     int sw, h_, b_;
-    pix_decomp(sg, segs_w, H, b_, h_, sw);
+    pix_decomp(seg, segs_w, H, b_, h_, sw);
     const int w0 = sw << 6;
-    __syncthreads();                                            // the previous run has been consumed
-    for (int i = threadIdx.x; i < 64 * (COUT / 8); i += NTHR) {  // dY run (zero beyond the row end)
-      const int p = i / (COUT / 8), c = i - p * (COUT / 8);
-      const bool ok = w0 + p < W;
-      *reinterpret_cast<uint4*>(ys + p * YP + c * 8) = ok ? *reinterpret_cast<const uint4*>(dy + ((long long)(b_ * H + h_) * W + w0 + p) * lddy + c * 8) : z4;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int i = threadIdx.x + k * NTHR;
+      pre[k] = make_uint4(0, 0, 0, 0);
+      if (i < NY) {
+        const int p = i / (COUT / 8), c = i - p * (COUT / 8);
+        if (w0 + p < W) pre[k] = *reinterpret_cast<const uint4*>(dy + ((long long)(b_ * H + h_) * W + w0 + p) * lddy + c * 8);
+      } else if (i < NY + NX) {
+        const int j = i - NY;
+        const int c = j % (CIN / 8), p = (j / (CIN / 8)) % XW, r = j / ((CIN / 8) * XW);
+        const int hh = h_ + r - R, ww = w0 + p - R;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) pre[k] = *reinterpret_cast<const uint4*>(x + ((long long)(b_ * H + hh) * W + ww) * ldx + c * 8);
+      }
     }
-    for (int i = threadIdx.x; i < XR * XW * (CIN / 8); i += NTHR) {   // X neighbourhood, zero padded
-      const int c = i % (CIN / 8), p = (i / (CIN / 8)) % XW, r = i / ((CIN / 8) * XW);
-      const int hh = h_ + r - R, ww = w0 + p - R;
-      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-      *reinterpret_cast<uint4*>(xs + (r * XW + p) * XP + c * 8) = ok ? *reinterpret_cast<const uint4*>(x + ((long long)(b_ * H + hh) * W + ww) * ldx + c * 8) : z4;
+  };
+  if ((long long)blockIdx.x < nsegs) load_run(blockIdx.x);
+  for (long long sg = blockIdx.x; sg < nsegs; sg += gridDim.x) {
+    __syncthreads();                                            // the previous run has been consumed
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int i = threadIdx.x + k * NTHR;
+      if (i < NY) {
+        const int p = i / (COUT / 8), c = i - p * (COUT / 8);
+        *reinterpret_cast<uint4*>(ys + p * YP + c * 8) = pre[k];
+      } else if (i < NY + NX) {
+        const int j = i - NY;
+        const int c = j % (CIN / 8), p = (j / (CIN / 8)) % XW, r = j / ((CIN / 8) * XW);
+        *reinterpret_cast<uint4*>(xs + (r * XW + p) * XP + c * 8) = pre[k];
+      }
     }
     __syncthreads();
+    if (sg + gridDim.x < nsegs) load_run(sg + gridDim.x);
     const int mat = lane >> 3, rr = lane & 7;
 #pragma unroll
     for (int ks_ = 0; ks_ < 4; ++ks_) {                         // 16-pixel K steps of the run
@@ -252,8 +324,7 @@ long long mid_wgrad_ws_bytes(int Cin, int Cout, int ks) { return (long long)kMid
 template <int CIN, int NT, int KS>
 static int mid_conv_launch_t(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, float* partials,
                              int* nparts_host, cudaStream_t st) {
-  constexpr int K = KS * KS * CIN, COUT = NT * 8;
-  const size_t smem = (size_t)COUT * (K + 8) * 2 + (size_t)8 * 16 * (COUT + 8) * 2 + (size_t)8 * 2 * COUT * 4;
+  const size_t smem = MidCfg<CIN, NT, KS>::smem;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_mid_mma<CIN, NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
