@@ -383,7 +383,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
           1 if use_batch_stats else 0, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _stream())
     y = out if out is not None else x.like(cout)
     pooled = Act.new(x.B, x.H // 2, x.W // 2, cout, dtype=x.t.dtype, device=dev) if pool else None
-    _call("ustrun_bn_act_fwd", raw.ptr, raw.ld, _ptr(scale), _ptr(shift), act, y.ptr, y.ld, pooled.ptr if pool else None,
+    _profiled("hbm_bn_act", raw.npix * cout * raw.t.element_size() * (2.25 if pool else 2.0), "ustrun_bn_act_fwd", raw.ptr, raw.ld, _ptr(scale), _ptr(shift), act, y.ptr, y.ld, pooled.ptr if pool else None,
           pooled.ld if pool else 0, x.dtype_code, x.B, x.H, x.W, cout, _stream())
 
     if ctx.need_grad:
@@ -397,14 +397,14 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
             G = y.g
             if pool and pooled.g is not None:
                 Gn = y.like() if y.parent is None else Act.new(y.B, y.H, y.W, y.C, dtype=y.t.dtype, device=dev)
-                _call("ustrun_maxpool_bwd", y.ptr, y.ld, pooled.g.ptr, pooled.g.ld, G.ptr if G is not None else None,
+                _profiled("hbm_maxpool_bwd", y.npix * y.C * y.t.element_size() * (3.25 if G is not None else 2.25), "ustrun_maxpool_bwd", y.ptr, y.ld, pooled.g.ptr, pooled.g.ld, G.ptr if G is not None else None,
                       G.ld if G is not None else 0, Gn.ptr, Gn.ld, y.dtype_code, y.B, y.H, y.W, y.C, _stream())
                 G = Gn
             if G is None:
                 return
             part = torch.empty(L.MAX_PARTS * 2 * cout, dtype=torch.float32, device=dev)
             np_ = ctypes.c_int(0)
-            _call("ustrun_bn_bwd_reduce", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), act,
+            _profiled("hbm_bn_bwd_reduce", raw.npix * cout * raw.t.element_size() * 2.0, "ustrun_bn_bwd_reduce", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), act,
                   raw.dtype_code, raw.npix, cout, _ptr(part), ctypes.byref(np_), _stream())
             n_parts, cnt = np_.value, float(raw.npix)
             coef = torch.empty(3 * cout, dtype=torch.float32, device=dev)
@@ -422,7 +422,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
               _call("ustrun_bn_bwd_finalize", _ptr(part), n_parts, cout, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
                   1 if (acc_g or acc_b) else 0, 1.0 / world if bn_sync is not None else 1.0, _ptr(coef), _stream())
             draw = raw.like()
-            _call("ustrun_bn_bwd_apply", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
+            _profiled("hbm_bn_bwd_apply", raw.npix * cout * raw.t.element_size() * 3.0, "ustrun_bn_bwd_apply", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
                   act, draw.ptr, draw.ld, raw.dtype_code, raw.npix, cout, _stream())
             if conv.bias is not None:
                 dbias, acc = sink.get(conv.bias)          # BN removes the mean: d/dbias == 0 exactly

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import _call, _ptr, _stream, mark_params_updated
+from .engine import _call, _profiled, _ptr, _stream, mark_params_updated
 
 
 class FusedSGDEMA:
@@ -78,7 +78,7 @@ class FusedSGDEMA:
     def step(self, lr, alpha=None, grad_scale=1.0, do_sgd=True):
         """SGD step with the gradients currently in the flat buffer, then (alpha given) EMA."""
         table = self._table()
-        _call("ustrun_sgd_ema_multi", _ptr(table), _ptr(self.blk_tensor), _ptr(self.blk_offset), self.nblocks, float(lr), self.momentum,
+        _profiled("hbm_sgd_ema", 28.0 * sum(p.numel() for p in self.params), "ustrun_sgd_ema_multi", _ptr(table), _ptr(self.blk_tensor), _ptr(self.blk_offset), self.nblocks, float(lr), self.momentum,
               self.weight_decay, float(alpha if alpha is not None else 0.0), float(grad_scale), 1 if do_sgd else 0,
               1 if alpha is not None else 0, _stream())
         if do_sgd:
