@@ -69,6 +69,29 @@ template <> struct Vec8<float> {
   }
 };
 
+// raw 8-element loads (kept unconverted in registers so that several independent loads can be issued back to back
+// before the first conversion: the streaming kernels batch 2-4 pixels per loop iteration by hand -- with a bounds check
+// per unrolled iteration the compiler serialises load -> use -> load and only one pixel's loads are in flight)
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void get(float (&v)[8]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+};
+
 // linear pixel index -> (b, h, w) with 32-bit arithmetic (64-bit div/mod costs ~100 instructions each;
 // every entry point checks B*H*W < 2^31)
 __device__ __forceinline__ void pix_decomp(long long p, int W, int H, int& b, int& h, int& w) {

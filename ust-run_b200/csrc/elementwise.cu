@@ -271,17 +271,35 @@ k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __restrict__ x, int l
     float sc[8], sh[8];
     Vec8<float>::load(scale + cg * 8, sc);
     Vec8<float>::load(shift + cg * 8, sh);
-#pragma unroll 4
-    for (long long p = (long long)blockIdx.x * lanes + tid / CG; p < npix; p += (long long)gridDim.x * lanes) {
+    auto accum = [&](const Raw8<T>& gr, const Raw8<T>& xr) {
       float gv[8], xv[8];
-      Vec8<T>::load(g + p * ldg + cg * 8, gv);
-      Vec8<T>::load(x + p * ldx + cg * 8, xv);
+      gr.get(gv);
+      xr.get(xv);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float gp = gv[k] * act_grad(fmaf(xv[k], sc[k], sh[k]), act);
         acc[k] += gp;
         acc[8 + k] = fmaf(gp, xv[k], acc[8 + k]);
       }
+    };
+    constexpr int UB = sizeof(T) == 2 ? 4 : 1;        // pixels per iteration: 8 independent 16-byte loads in flight per thread (bf16)
+    const long long step = (long long)gridDim.x * lanes;
+    long long p = (long long)blockIdx.x * lanes + tid / CG;
+    for (; p + (UB - 1) * step < npix; p += UB * step) {
+      Raw8<T> gr[UB], xr[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        gr[u].load(g + (p + u * step) * ldg + cg * 8);
+        xr[u].load(x + (p + u * step) * ldx + cg * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) accum(gr[u], xr[u]);
+    }
+    for (; p < npix; p += step) {
+      Raw8<T> gr, xr;
+      gr.load(g + p * ldg + cg * 8);
+      xr.load(x + p * ldx + cg * 8);
+      accum(gr, xr);
     }
   }
   // block totals in two phases through one 8 KB buffer (sum g', then sum g'*x): with <= 9 KB of shared memory two of
@@ -370,17 +388,34 @@ k_bn_bwd_apply(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ld
   Vec8<float>::load(shift + cg * 8, sh);
   const long long pstep = stride / CG;             // stride % CG == 0: no division inside the loop
   (void)n;
-#pragma unroll 2
-  for (long long p = i / CG; p < npix; p += pstep) {
+  auto apply = [&](const Raw8<T>& gr, const Raw8<T>& xr, long long p) {
     float gv[8], xv[8], o[8];
-    Vec8<T>::load(g + p * ldg + cg * 8, gv);
-    Vec8<T>::load(x + p * ldx + cg * 8, xv);
+    gr.get(gv);
+    xr.get(xv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float gp = gv[k] * act_grad(fmaf(xv[k], sc[k], sh[k]), act);
       o[k] = fmaf(a[k], gp, fmaf(cx[k], xv[k], c0[k]));
     }
     Vec8<T>::store(dx + p * lddx + cg * 8, o);
+  };
+  constexpr int UB = sizeof(T) == 2 ? 3 : 1;          // pixels per iteration: 6 independent 16-byte loads in flight per thread (bf16)
+  long long p = i / CG;
+  for (; p + (UB - 1) * pstep < npix; p += UB * pstep) {
+    Raw8<T> gr[UB], xr[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      gr[u].load(g + (p + u * pstep) * ldg + cg * 8);
+      xr[u].load(x + (p + u * pstep) * ldx + cg * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) apply(gr[u], xr[u], p + u * pstep);
+  }
+  for (; p < npix; p += pstep) {
+    Raw8<T> gr, xr;
+    gr.load(g + p * ldg + cg * 8);
+    xr.load(x + p * ldx + cg * 8);
+    apply(gr, xr, p);
   }
 }
 
