@@ -220,6 +220,21 @@ int ustrun_fft_amp_mix(const float* src, const float* trg, const double* ratio, 
 int ustrun_hardness(const unsigned char* stu_pl, const unsigned char* tea_pl, int B, int H, int W, int mode, int first_epoch,
                     unsigned int* workspace, double* hardness, double* dice, int* lq_idx, void* stream);
 
+/* ---- evaluation helpers --------------------------------------------------
+ * ustrun_encode_labels: the label encodings of train.py:590-608 / :281-288 and train_mnms.py:549-556 on the float32
+ *   label image the data loader yields.  mode 0: y == 0 (prostate); 1: y == 255 (BUSI); 2: two planes {y == 0, y <= 128}
+ *   (fundus) -> out [B,2,H,W]; 3: y [B,H,W,3], label 1/2/3 where channel 0/1/2 == 255 (M&Ms).  out: uint8.
+ * ustrun_predict: train.py:295-302: softmax branch argmax of the softmax PROBABILITIES (first maximum) -> [B,H,W];
+ *   sigmoid branch sigmoid(x) >= 0.5 -> [B,C,H,W].  logits fp32 NCHW, pred uint8.
+ * ustrun_seg_metrics: per label part, batch means of the reference's Dice (utils/metrics.py:114-146 via dice_coeff*,
+ *   train.py:303) and of medpy.metric.binary dc / jc (train.py:307-311; medpy is not vendored: dc = 2I/(S+G), 0 if empty;
+ *   jc = I/|union|, 0 where medpy raises on an empty union).  mode as in ustrun_hardness.  workspace: unsigned int[B*9];
+ *   out: double[3][parts] = {dice, dc, jc}.  hd95 / asd stay on the host (medpy). */
+int ustrun_encode_labels(const float* y, int mode, int B, int H, int W, unsigned char* out, void* stream);
+int ustrun_predict(const float* logits, int sigmoid, int B, int C, int H, int W, unsigned char* pred, void* stream);
+int ustrun_seg_metrics(const unsigned char* pred, const unsigned char* target, int B, int H, int W, int mode, unsigned int* workspace,
+                       double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,14 +305,14 @@ k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __restrict__ x, int l
   // block totals in two phases through one 8 KB buffer (sum g', then sum g'*x): with <= 9 KB of shared memory two of
   // these blocks fit next to a resident weight-gradient CTA (200 KB) that runs concurrently on the side stream
   const int lanes = 256 / CG;
-  float s1r[4], s2r[4];                  // C <= 1024: a thread finalises at most 4 channels
+  float s1r[8], s2r[8];                  // C <= 2048 (C/8 <= 256 channel groups): a thread finalises at most 8 channels
 #pragma unroll
   for (int ph = 0; ph < 2; ++ph) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) sm[k * 256 + tid] = acc[ph * 8 + k];
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int c = tid + i * 256;
       float s = 0.f;
       if (c < C) {
@@ -324,7 +324,7 @@ k_bn_bwd_reduce(const T* __restrict__ g, int ldg, const T* __restrict__ x, int l
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     const int c = tid + i * 256;
     if (c < C) {
       partials[(size_t)blockIdx.x * 2 * C + c] = s1r[i];

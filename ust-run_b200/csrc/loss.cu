@@ -426,6 +426,67 @@ __global__ void k_hardness_finalize(const unsigned int* __restrict__ counts, int
   *lq_idx = best;
 }
 
+// ------------------------------------------------------------------------------------------
+// evaluation helpers: label encodings, predictions, per-part segmentation metrics
+// ------------------------------------------------------------------------------------------
+// train.py:590-608 / 281-288 and train_mnms.py:549-556.  mode 0: y == 0 (prostate); 1: y == 255 (BUSI);
+// 2: two planes {y == 0, y <= 128} (fundus: cup, disc); 3: y is [B,H,W,3], label = 1/2/3 where channel 0/1/2 == 255,
+// later channels override (M&Ms).  y: the float32 label image the data loader yields.
+__global__ void __launch_bounds__(256)
+k_encode_labels(const float* __restrict__ y, int mode, int B, int HW, uint8_t* __restrict__ out) {
+  const long long n = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (mode == 0) out[i] = y[i] == 0.f;
+    else if (mode == 1) out[i] = y[i] == 255.f;
+    else if (mode == 2) {
+      const long long b = i / HW, p = i - b * HW;
+      out[(b * 2) * HW + p] = y[i] == 0.f;
+      out[(b * 2 + 1) * HW + p] = y[i] <= 128.f;
+    } else {
+      uint8_t l = y[i * 3] == 255.f ? 1 : 0;
+      if (y[i * 3 + 1] == 255.f) l = 2;
+      if (y[i * 3 + 2] == 255.f) l = 3;
+      out[i] = l;
+    }
+  }
+}
+// softmax branch: torch.max(torch.softmax(output, 1), 1)[1] (first maximum of the PROBABILITIES)
+template <int C>
+__global__ void __launch_bounds__(256) k_predict_softmax(const float* __restrict__ logits, int B, int HW, uint8_t* __restrict__ pred) {
+  const long long n = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    float x[MAXC], pr[MAXC], conf;
+    int arg;
+#pragma unroll
+    for (int c = 0; c < C; ++c) x[c] = logits[(b * C + c) * HW + p];
+    softmax_argmax<C>(x, conf, arg, pr);
+    pred[i] = (uint8_t)arg;
+  }
+}
+// sigmoid branch: torch.sigmoid(output).ge(0.5)
+__global__ void __launch_bounds__(256) k_predict_sigmoid(const float* __restrict__ logits, long long n, uint8_t* __restrict__ pred) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    pred[i] = sigmoidf_aten(logits[i]) >= 0.5f;
+}
+// batch means per part of: Dice as utils/metrics.py:114-146, and medpy.metric.binary dc = 2I/(S+G) (0 when S+G == 0)
+// and jc = I/(S+G-I) (medpy raises ZeroDivisionError for an empty union; 0 here) -- train.py:304-320
+__global__ void k_seg_metrics_finalize(const unsigned int* __restrict__ counts, int B, int parts, double* __restrict__ out) {
+  const int p = threadIdx.x;
+  if (p >= parts) return;
+  double dice = 0.0, dc = 0.0, jc = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const unsigned int* c = counts + ((size_t)b * parts + p) * 3;
+    const double S = (double)c[0], G = (double)c[1], I = (double)c[2];
+    dice += (c[0] == 0 && c[1] == 0) ? 0.0 : (2.0 * I + 1.0) / (1.001 + S + G);
+    dc += (S + G) > 0.0 ? 2.0 * I / (S + G) : 0.0;
+    jc += (S + G - I) > 0.0 ? I / (S + G - I) : 0.0;
+  }
+  out[p] = dice / (double)B;               // sum(all_dice) / len(all_dice): sequential sum, then one division
+  out[parts + p] = dc / (double)B;
+  out[2 * parts + p] = jc / (double)B;
+}
+
 }  // namespace ustrun
 
 using namespace ustrun;
@@ -567,6 +628,32 @@ int ustrun_hardness(const uint8_t* stu_pl, const uint8_t* tea_pl, int B, int H, 
   k_hardness_counts<<<dim3(B, parts), 256, 0, (cudaStream_t)stream>>>(stu_pl, tea_pl, H * W, mode, parts, workspace);
   k_hardness_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, B, parts, first_epoch, hardness, dice, lq_idx);
   return check_launch("hardness");
+}
+
+int ustrun_encode_labels(const float* y, int mode, int B, int H, int W, unsigned char* out, void* stream) {
+  USTRUN_REQUIRE(y && out && B > 0 && H > 0 && W > 0 && mode >= 0 && mode <= 3, "encode_labels: bad args");
+  const long long n = (long long)B * H * W;
+  k_encode_labels<<<loss_grid(n), 256, 0, (cudaStream_t)stream>>>(y, mode, B, H * W, out);
+  return check_launch("encode_labels");
+}
+int ustrun_predict(const float* logits, int sigmoid, int B, int C, int H, int W, unsigned char* pred, void* stream) {
+  USTRUN_REQUIRE(logits && pred && B > 0 && C > 0 && H > 0 && W > 0, "predict: bad args");
+  if (sigmoid) {
+    const long long n = (long long)B * C * H * W;
+    k_predict_sigmoid<<<loss_grid(n), 256, 0, (cudaStream_t)stream>>>(logits, n, pred);
+  } else {
+    USTRUN_REQUIRE(C >= 2 && C <= 8, "predict: softmax branch supports 2..8 classes");
+    const long long n = (long long)B * H * W;
+    DISPATCH_C(C, (k_predict_softmax<kC><<<loss_grid(n), 256, 0, (cudaStream_t)stream>>>(logits, B, H * W, pred)));
+  }
+  return check_launch("predict");
+}
+int ustrun_seg_metrics(const uint8_t* pred, const uint8_t* target, int B, int H, int W, int mode, unsigned int* workspace, double* out, void* stream) {
+  USTRUN_REQUIRE(pred && target && workspace && out && B > 0 && H > 0 && W > 0 && mode >= 0 && mode <= 2, "seg_metrics: bad args");
+  const int parts = mode == 0 ? 1 : (mode == 1 ? 2 : 3);
+  k_hardness_counts<<<dim3(B, parts), 256, 0, (cudaStream_t)stream>>>(pred, target, H * W, mode, parts, workspace);
+  k_seg_metrics_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, B, parts, out);
+  return check_launch("seg_metrics");
 }
 
 }  // extern "C"

@@ -71,6 +71,9 @@ _SIGS = {
     "ustrun_sgd_ema_multi": [p, p, p, i32, f32, f32, f32, f32, f32, i32, i32, p],
     "ustrun_fft_amp_mix": [p, p, p, f64, p, i32, i32, i32, i32, p, i64, p],
     "ustrun_hardness": [p, p, i32, i32, i32, i32, i32, p, p, p, p, p],
+    "ustrun_encode_labels": [p, i32, i32, i32, i32, p, p],
+    "ustrun_predict": [p, i32, i32, i32, i32, i32, p, p],
+    "ustrun_seg_metrics": [p, p, i32, i32, i32, i32, p, p, p],
 }
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
