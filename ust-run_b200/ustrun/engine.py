@@ -353,7 +353,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
     Reference: unet_parts.py:15-21,34 / unet.py:52-72,96-117."""
     ks = conv.kernel_size[0]
     cout = conv.out_channels
-    wf, wd = packed.get(conv.weight, need_wd=ctx.need_grad)
+    wf, wd = packed.get(conv.weight, need_wd=ctx.need_grad or conv.weight.requires_grad)
     dev = x.t.device
     raw = x.like(cout)
     training = ctx.training and bn.training if hasattr(bn, "training") else ctx.training
@@ -456,7 +456,7 @@ def _assign_grad(x: Act, gx: Act):
 def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
     """nn.ConvTranspose2d(k2, s2) + bias, written straight into ``out`` (usually the second half
     of the decoder's concat buffer): unet_parts.py:53,57,62-67."""
-    wf, wd = packed.get(up.weight, transposed=True, need_wd=ctx.need_grad)
+    wf, wd = packed.get(up.weight, transposed=True, need_wd=ctx.need_grad or up.weight.requires_grad)
     cin, cout = up.in_channels, up.out_channels
     impl = _impl_for(cin, cout, x.dtype_code)
     _call("ustrun_convT2x2_fwd", impl, x.ptr, x.ld, _ptr(wf), _ptr(up.bias), out.ptr, out.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream())
@@ -511,7 +511,7 @@ def head_conv(ctx: Ctx, x: Act, conv, packed: PackedConv):
     Returns (logits, backward_fn(dlogits, sink))."""
     ks = conv.kernel_size[0]
     cout = conv.out_channels
-    wf, wd = packed.get(conv.weight, need_wd=ctx.need_grad)
+    wf, wd = packed.get(conv.weight, need_wd=ctx.need_grad or conv.weight.requires_grad)
     logits = torch.empty((x.B, cout, x.H, x.W), dtype=torch.float32, device=x.t.device)
     _raw_conv(x, wf, conv.bias, None, ks, out_nchw=logits)
 
