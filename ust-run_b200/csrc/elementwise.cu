@@ -338,11 +338,24 @@ __global__ void k_bn_bwd_finalize(const float* __restrict__ partials, int nparts
                                   float* dbeta, int accumulate, float param_grad_scale, float* coef) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int r = lane; r < nparts; r += 32) {
+  // up to 888 partial rows: four independent accumulator pairs keep eight loads in flight per lane (a single dependent
+  // chain made this tiny kernel 14 us long, 72 times per step)
+  double s1 = 0.0, s2 = 0.0, t1 = 0.0, t2 = 0.0, u1 = 0.0, u2 = 0.0, v1 = 0.0, v2 = 0.0;
+  int r = lane;
+  for (; r + 96 < nparts; r += 128) {
+    const float a0 = partials[(size_t)r * 2 * C + c], b0 = partials[(size_t)r * 2 * C + C + c];
+    const float a1 = partials[(size_t)(r + 32) * 2 * C + c], b1 = partials[(size_t)(r + 32) * 2 * C + C + c];
+    const float a2 = partials[(size_t)(r + 64) * 2 * C + c], b2 = partials[(size_t)(r + 64) * 2 * C + C + c];
+    const float a3 = partials[(size_t)(r + 96) * 2 * C + c], b3 = partials[(size_t)(r + 96) * 2 * C + C + c];
+    s1 += (double)a0; s2 += (double)b0; t1 += (double)a1; t2 += (double)b1;
+    u1 += (double)a2; u2 += (double)b2; v1 += (double)a3; v2 += (double)b3;
+  }
+  for (; r < nparts; r += 32) {
     s1 += (double)partials[(size_t)r * 2 * C + c];
     s2 += (double)partials[(size_t)r * 2 * C + C + c];
   }
+  s1 += t1 + (u1 + v1);
+  s2 += t2 + (u2 + v2);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);

@@ -212,7 +212,8 @@ k_wgrad_reduce(const float* __restrict__ ws, int splits, int Mo, int Nin, float*
     for (int t = 0; t < TAPS; ++t) acc[t] = 0.f;
     if (lane < nc) {
       const float* src = ws + ((size_t)m * TAPS) * Nin + c0 + lane;
-      for (int k = 0; k < splits; ++k) {
+#pragma unroll 4
+      for (int k = 0; k < splits; ++k) {               // up to ~49 splits for the 64-channel layers: keep 4 x TAPS loads in flight
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) acc[t] += src[(size_t)k * n + (size_t)t * Nin];
       }
