@@ -194,7 +194,7 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()        # the user reads the loss every step
 
     # one cudaMalloc up front instead of ~40 during the first 20 steps (cfg5 needs > 100 GB of activations + workspaces)
-    pool = E.reserve_pool(fraction=0.85 if args.workload == "cfg5" else 0.5, cap=160 << 30)
+    pool = E.reserve_pool(fraction=0.6 if args.workload == "cfg5" else 0.5, cap=160 << 30)
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local)

@@ -84,6 +84,7 @@ def _profiled(cls, flops, name, *args):
 _WGRAD_OVERLAP = os.environ.get("USTRUN_WGRAD_OVERLAP", "1") == "1"
 _WGRAD_AFTER_DGRAD = os.environ.get("USTRUN_WGRAD_AFTER_DGRAD", "0") == "1"
 _SIDE: Dict[int, "torch.cuda.Stream"] = {}
+_SIDE_MAX_BYTES = int(os.environ.get("USTRUN_WGRAD_OVERLAP_MAX_BYTES", str(768 << 20)))
 
 
 def set_wgrad_overlap(flag: bool) -> None:
@@ -105,7 +106,9 @@ def on_side_stream(fn: Callable, tensors) -> None:
     """Run ``fn`` (which enqueues kernels reading ``tensors``) on the weight-gradient stream, ordered after
     everything enqueued so far on the current stream."""
     side = _side_stream()
-    if side is None:
+    # record_stream keeps the operands out of the allocator until the side stream has caught up: for multi-GB activations
+    # (cfg5: 2 GB per layer-1 tensor) that inflates the footprint by tens of GB for no gain, so those run in line
+    if side is None or sum(t.numel() * t.element_size() for t in tensors) > _SIDE_MAX_BYTES:
         fn()
         return
     ev = torch.cuda.Event()
