@@ -183,7 +183,6 @@ struct TcConvParams {
 
 constexpr int kEpiBar0 = 1, kEpiBar1 = 2;
 constexpr uint32_t kStageA = 128 * 128;        // 128 pixel rows x 128 B
-constexpr uint32_t kStagingBytes = 2 * 16384;
 
 // ROW mode (3x3 conv, tile = 128 consecutive pixels of ONE image row): a stage holds one (dy, channel chunk)
 // box of 136 pixels starting at w0-1 plus the weights of the three dx taps; the three dx taps are three
@@ -272,20 +271,20 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
               }
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
-          continue;
-        }
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          int dh = 0, dw = 0;
-          const CUtensorMap* mA = &mapA0;
-          if (p.tap_mode == TAP_CONV3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
-          else if (p.tap_mode == TAP_PERMAP) mA = tap == 0 ? &mapA0 : (tap == 1 ? &mapA1 : (tap == 2 ? &mapA2 : &mapA3));
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * stage_stride;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)(p.TH * p.TW * 128) + (RESB ? 0u : Cfg::stageB));
-            tma_load_4d(sa, mA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, b);
-            if constexpr (!RESB) tma_load_2d(sa + Cfg::stageA, &mapW, &full_bar[stage], (tap * kchunks + kc) * 64, n0);
-            if (++stage == S) { stage = 0; phase ^= 1; }
+        } else {
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            int dh = 0, dw = 0;
+            const CUtensorMap* mA = &mapA0;
+            if (p.tap_mode == TAP_CONV3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+            else if (p.tap_mode == TAP_PERMAP) mA = tap == 0 ? &mapA0 : (tap == 1 ? &mapA1 : (tap == 2 ? &mapA2 : &mapA3));
+            for (int kc = 0; kc < kchunks; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * stage_stride;
+              mbar_expect_tx(&full_bar[stage], (uint32_t)(p.TH * p.TW * 128) + (RESB ? 0u : Cfg::stageB));
+              tma_load_4d(sa, mA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, b);
+              if constexpr (!RESB) tma_load_2d(sa + Cfg::stageA, &mapW, &full_bar[stage], (tap * kchunks + kc) * 64, n0);
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
