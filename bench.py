@@ -105,9 +105,9 @@ def make_models(model, c, k):
 
 
 def conv_flops_per_image(model, c, k, H, W):
-    from oracle import unet_ref as U
     if model == "unet_a":
-        return U.conv_flops_unet_a(c, k, H, W)
+        from ustrun.synth import conv_flops_unet_a
+        return conv_flops_unet_a(c, k, H, W)
     # UNet-B: trace from the layer table (3 convs per ConvD, conv1/conv2(1x1)/conv3 per ConvU, 3x3 head)
     n, f, h, w, cin = 16, 0, H, W, c
     for i in range(5):
@@ -131,7 +131,7 @@ def conv_flops_per_image(model, c, k, H, W):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import ssl_step_ref as S       # synthetic input generator only (shared with the tests)
+    from ustrun import synth as S               # synthetic input generator (product side; no oracle on this arm)
     from ustrun import engine as E
     from ustrun.step import SSLTrainer
 

@@ -61,6 +61,14 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("oracle/", "").lower() or f == "__init__.py" or "import oracle" not in text, f
                 assert "from oracle" not in text and "import oracle" not in text, f"{f} imports the oracle"
+    # tools/ are product-side utilities too; bench.py may use the oracle only in its CPU legs
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            text = open(os.path.join(ROOT, "tools", f)).read()
+            assert "from oracle" not in text and "import oracle" not in text, f"tools/{f} imports the oracle"
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    gpu_arm = bench[bench.index("def run_ours("):bench.index("def cpu_step_time(")]
+    assert gpu_arm and "oracle" not in gpu_arm.replace("no oracle on this arm", ""), "bench.py GPU arm touches the oracle"
 
 
 def test_state_dict_layout_matches_oracle_init():
@@ -98,3 +106,19 @@ def test_error_conventions():
         d(torch.zeros(2, 8, 4), torch.tensor([0]))
     with pytest.raises(TypeError):
         B.UNet(norm="dsbn")         # upstream: num_domains=None -> TypeError at construction
+
+
+def test_synthetic_workload_matches_test_generator():
+    """bench.py's GPU arm and tools/ draw their inputs from ustrun.synth (the measured arm never imports the
+    oracle); the cpu_baseline / reference arm draws from the oracle's generator.  Same seeds -> same workload."""
+    import torch
+    from oracle import ssl_step_ref as S
+    from oracle import unet_ref as U
+    from ustrun import synth
+    for br in ("softmax", "sigmoid"):
+        a = synth.synthetic_batch(3, 3, 32, 48, 2, 3, seed=11, branch=br)
+        b = S.synthetic_batch(3, 3, 32, 48, 2, 3, seed=11, branch=br)
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+    assert synth.conv_flops_unet_a(1, 2, 384, 384) == U.conv_flops_unet_a(1, 2, 384, 384)

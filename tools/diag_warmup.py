@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ust-run_b200"))
 import torch
 import bench
-from oracle import ssl_step_ref as S
+from ustrun import synth as S
 from ustrun import engine as E
 from ustrun.step import SSLTrainer
 t00 = time.time()

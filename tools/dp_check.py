@@ -8,7 +8,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ust-run_b200"))
 import torch, torch.distributed as dist
-from oracle import ssl_step_ref as S
+from ustrun import synth as S
 from ustrun import engine as E
 from ustrun.step import SSLTrainer
 from ustrun.dp import DataParallel
