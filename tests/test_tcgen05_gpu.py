@@ -24,6 +24,12 @@ SHAPES = [  # B, Cin, Cout, H, W
     (1, 64, 64, 4, 96),        # row-mode wgrad with 48-pixel segments
     (1, 128, 64, 4, 48),       # row-mode wgrad, swapped operands (Cout=64 < Cin)
     (1, 256, 256, 24, 24),     # row-mode wgrad, one zero-padded 32-pixel segment per row
+    (8, 64, 1024, 24, 24),     # tile planner: M tiles of two 8x8 boxes (36 full tiles instead of 40 ragged ones), N=256
+    (8, 128, 512, 24, 24),     # tile planner: two-box tiles and the narrower N=128 tile (all SMs get one tile)
+    (5, 64, 2048, 12, 12),     # two-box tiles, 12x5 boxes (60 of 64 rows, last box of an image 2 rows), odd box count
+    (7, 64, 2048, 12, 24),     # two-box tiles, 5x12 boxes ragged in W, odd box count, N=256
+    (1, 64, 64, 18, 16),       # row-mode wgrad with 4 image rows per stage, last row group half empty
+    (2, 64, 128, 5, 24),       # row-mode wgrad with 2 image rows per stage, odd H
 ]
 
 
@@ -73,7 +79,8 @@ def test_tc_conv_fwd_stats_dgrad_wgrad(B, cin, cout, H, W, ks):
     assert rel_err(dw, 2 * ref_dw) < 2e-3
 
 
-@pytest.mark.parametrize("B,cin,cout,H,W", [(2, 128, 64, 16, 16), (1, 512, 256, 12, 12), (2, 64, 64, 24, 8)])
+@pytest.mark.parametrize("B,cin,cout,H,W", [(2, 128, 64, 16, 16), (1, 512, 256, 12, 12), (2, 64, 64, 24, 8),
+                                            (8, 1024, 512, 24, 24)])      # bottleneck up-conv: two-box tiles fwd (N=128) and dgrad (N=256)
 def test_tc_conv_transpose(B, cin, cout, H, W):
     from ustrun import _lib as L
     E = _setup()

@@ -175,11 +175,23 @@ struct TcConvParams {
   int ntaps, tap_mode;
   int TW, TH, tiles_w, tiles_h;
   int m_tiles, n_tiles, ctas_per_n;
+  int halves, units;     // halves == 2: an M tile is two independent TW x TH (<= 64 pixel) boxes, rows 0-63 / 64-127;
+                         // units = number of boxes (= m_tiles when halves == 1)
   float* partials;       // [ctas_per_n][2][Cout] or null
   const float* bias;     // [Cout] or null
   int stages, nstaging;  // RESB only: depth of the activation ring / number of 16 KB store staging buffers
   uint32_t wres_bytes;   // RESB only: bytes of the resident weight block (ntaps * Cin/64 slots of BN x 128 B)
 };
+
+struct BoxCoord { int w0, h0, b; };
+__device__ __forceinline__ BoxCoord box_coord(const TcConvParams& p, int unit) {
+  BoxCoord c;
+  const int r = unit / p.tiles_w;
+  c.w0 = (unit - r * p.tiles_w) * p.TW;
+  c.b = r / p.tiles_h;
+  c.h0 = (r - c.b * p.tiles_h) * p.TH;
+  return c;
+}
 
 constexpr int kEpiBar0 = 1, kEpiBar1 = 2;
 constexpr uint32_t kStageA = 128 * 128;        // 128 pixel rows x 128 B
@@ -255,8 +267,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       }
       int stage = 0; uint32_t phase = 0;
       for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n) {
-        const int txi = mt % p.tiles_w, tyi = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = txi * p.TW, h0 = tyi * p.TH;
+        const BoxCoord c0 = box_coord(p, mt * p.halves);
+        const int w0 = c0.w0, h0 = c0.h0, b = c0.b;
         if constexpr (ROW) {
           for (int dy = 0; dy < 3; ++dy)
             for (int kc = 0; kc < kchunks; ++kc) {
@@ -272,6 +284,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
         } else {
+          // second 64-pixel box of the tile (rows 64..127 of the A stage); the last tile may have only one
+          const bool two = p.halves == 2 && mt * 2 + 1 < p.units;
+          const BoxCoord c1 = box_coord(p, two ? mt * 2 + 1 : 0);
+          const uint32_t tx_bytes = (uint32_t)(p.TH * p.TW * 128) * (two ? 2u : 1u) + (RESB ? 0u : Cfg::stageB);
           for (int tap = 0; tap < p.ntaps; ++tap) {
             int dh = 0, dw = 0;
             const CUtensorMap* mA = &mapA0;
@@ -280,8 +296,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             for (int kc = 0; kc < kchunks; ++kc) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * stage_stride;
-              mbar_expect_tx(&full_bar[stage], (uint32_t)(p.TH * p.TW * 128) + (RESB ? 0u : Cfg::stageB));
+              mbar_expect_tx(&full_bar[stage], tx_bytes);
               tma_load_4d(sa, mA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, b);
+              if (two) tma_load_4d(sa + kStageA / 2, mA, &full_bar[stage], kc * 64, c1.w0 + dw, c1.h0 + dh, c1.b);
               if constexpr (!RESB) tma_load_2d(sa + Cfg::stageA, &mapW, &full_bar[stage], (tap * kchunks + kc) * 64, n0);
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
@@ -362,11 +379,18 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     for (int mt = cta_j; mt < p.m_tiles; mt += p.ctas_per_n, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int txi = mt % p.tiles_w, tyi = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
-      const int w0 = txi * p.TW, h0 = tyi * p.TH;
-      const int th = row / p.TW, tw = row - th * p.TW;
-      const bool valid = (row < p.TH * p.TW) && (h0 + th < p.H) && (w0 + tw < p.W);
-      const bool tile_partial = (p.TH * p.TW < 128) || (h0 + p.TH > p.H) || (w0 + p.TW > p.W);
+      // box this row belongs to (a warp's 32 rows always share one) and its pixel inside the box
+      const int hsel = p.halves == 2 ? (row >> 6) : 0;
+      const int within = p.halves == 2 ? (row & 63) : row;
+      const int unit = mt * p.halves + hsel;
+      const bool unit_ok = unit < p.units;
+      const BoxCoord cr = box_coord(p, unit_ok ? unit : 0);
+      const int th = within / p.TW, tw = within - th * p.TW;
+      const bool valid = unit_ok && (within < p.TH * p.TW) && (cr.h0 + th < p.H) && (cr.w0 + tw < p.W);
+      const bool tile_partial = !__all_sync(0xffffffffu, valid);         // warp-uniform: only warps with masked rows pay for it
+      const BoxCoord s0 = box_coord(p, mt * p.halves);                     // store coordinates of the tile's box(es)
+      const bool two = p.halves == 2 && mt * 2 + 1 < p.units;
+      const BoxCoord s1 = box_coord(p, two ? mt * 2 + 1 : 0);
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
 #pragma unroll
@@ -416,7 +440,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         named_bar_sync(kEpiBar1, 128);
         if (q == 0) {                 // bulk-group state is per thread: elect.sync picks the same lane for the same mask every time
           if (elect_one()) {
-            tma_store_4d(&mapO, stg, n0 + c64 * 64, w0, h0, b);
+            tma_store_4d(&mapO, stg, n0 + c64 * 64, s0.w0, s0.h0, s0.b);
+            if (two) tma_store_4d(&mapO, stg + kStageA / 2, n0 + c64 * 64, s1.w0, s1.h0, s1.b);
             tma_store_commit();
           }
           __syncwarp();
@@ -585,30 +610,75 @@ struct TcWgradRowParams {
   int B, H, W;
   int Mo, Nn;                 // valid channels on the M side / N side
   int TW, segs_w, nsegs;      // row segments
+  int R, hgroups;             // image rows per K segment (R * TW <= 64: narrow feature maps put several rows in a stage)
+  int nstages;                // ring depth (<= 8) and stage stride: sized on the host from TW and R
+  uint32_t stage_bytes;
   int m_tiles, n_tiles, splits, segs_per_split;
   int flip;                   // 1: operands swapped (M side = x, N side = dy shifted by -(tap)): tap index 8 - t
   float* ws;                  // [splits][Mo][9 * Nn]
 };
 template <int BN> struct WgRowCfg {
-  static constexpr uint32_t stageA = 2 * 64 * 128;                 // two 64-channel atoms x <= 64 pixels
-  static constexpr uint32_t atomB = 72 * 128;                      // <= 72 pixel rows per 64-channel atom
-  static constexpr uint32_t stageB = (BN / 64) * atomB;
-  static constexpr uint32_t stage = stageA + stageB;
-  static constexpr int stages = BN == 128 ? 6 : 8;
   static constexpr uint32_t tmem_cols = BN == 128 ? 512 : 256;
-  static constexpr uint32_t smem = stages * stage + 1024 + 1024;
+  // a stage = two M-side atoms of R x TW pixels + BN/64 N-side atoms of R x (TW+8) pixels (128 B per pixel)
+  static uint32_t stage_bytes(int TW, int R) { return (uint32_t)(2 * R * TW + (BN / 64) * R * (TW + 8)) * 128u; }
+  static int stages(int TW, int R) {
+    int n = (int)((232448u - 2048u) / stage_bytes(TW, R));
+    return n > 8 ? 8 : n;
+  }
+  static uint32_t smem(int TW, int R) { return (uint32_t)stages(TW, R) * stage_bytes(TW, R) + 1024 + 1024; }
 };
+
+// MMA stream of k_tc_wgrad_row for KS K-slices (16 pixels each) per image row.  The issuing thread is the critical path
+// when a stage holds only 6..12 MMAs of 48..64 cycles: with run-time trip counts nvcc emitted ~12 uniform-datapath
+// instructions (R2UR, 64-bit adds, predicate logic) per MMA and the tensor pipe idled 40 % of the time (ncu:
+// sm__pipe_tensor_cycles_active 61 %, the MMA warp never waiting on a full barrier).  Everything here is
+// straight-line: constant descriptor offsets, accumulate flag folded except for the first slice of a row.
+template <int BN, int KS>
+__device__ __forceinline__ void wg_row_mma_loop(const TcWgradRowParams& p, uint32_t tmem_base, uint64_t* full_bar, uint64_t* empty_bar,
+                                                uint64_t a_first, uint64_t b_first, int sg_begin, int sg_end) {
+  constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+  constexpr uint32_t idesc3 = make_idesc(192, 1, 1);
+  const uint64_t stride_d = (uint64_t)p.stage_bytes >> 4;
+  const uint64_t rowA = (uint64_t)(p.TW * 8), rowB = (uint64_t)((p.TW + 8) * 8);      // one image row, in 16-byte units
+  const int S = p.nstages, R = p.R;
+  uint64_t a_cur = a_first, b_cur = b_first;
+  int stage = 0; uint32_t phase = 0;
+  uint32_t acc_first = 0;                               // 0 only for the very first slice of each accumulator
+  for (int sg = sg_begin; sg < sg_end; ++sg) {
+    mbar_wait(&full_bar[stage], phase);
+    tc_fence_after();
+    uint64_t ar = a_cur, br = b_cur;
+    for (int r = 0; r < R; ++r) {                      // each image row of the stage is its own K run with its own halo
+      if constexpr (BN == 64) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k)                   // 16 pixel rows = 2 KB per K slice
+          tc_mma_bf16(tmem_base, ar + (uint64_t)(k * 128), br + (uint64_t)(k * 128), idesc3, k == 0 ? acc_first : 1u);
+      } else {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+          for (int k = 0; k < KS; ++k)                 // dx shifts the N-side view by one pixel row (128 B)
+            tc_mma_bf16(tmem_base + dx * BN, ar + (uint64_t)(k * 128), br + (uint64_t)(dx * 8 + k * 128), idesc, k == 0 ? acc_first : 1u);
+      }
+      acc_first = 1u;
+      ar += rowA; br += rowB;
+    }
+    tc_commit(&empty_bar[stage]);
+    a_cur += stride_d; b_cur += stride_d;
+    if (++stage == S) { stage = 0; phase ^= 1; a_cur = a_first; b_cur = b_first; }
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 k_tc_wgrad_row(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcWgradRowParams p) {
   using Cfg = WgRowCfg<BN>;
-  constexpr int S = Cfg::stages;
+  const int S = p.nstages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + S * Cfg::stage);
-  uint64_t* empty_bar = full_bar + S;
-  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)S * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
   uint32_t* tmem_holder = (uint32_t*)(tfull_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -619,7 +689,8 @@ k_tc_wgrad_row(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int split = wi;
   const int sg_begin = split * p.segs_per_split;
   const int sg_end = min(sg_begin + p.segs_per_split, p.nsegs);
-  const uint32_t atomA = (uint32_t)p.TW * 128, atomB = (uint32_t)(p.TW + 8) * 128;
+  const uint32_t atomA = (uint32_t)(p.R * p.TW) * 128, atomB = (uint32_t)(p.R * (p.TW + 8)) * 128;
+  const uint32_t stageA = 2 * atomA;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
@@ -638,48 +709,34 @@ k_tc_wgrad_row(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx = 2 * atomA + (BN / 64) * atomB;
+      // segment -> (image, row group, row segment), walked incrementally: no integer division on the per-stage path
+      int ws_ = sg_begin % p.segs_w, hg = (sg_begin / p.segs_w) % p.hgroups, b = sg_begin / (p.segs_w * p.hgroups);
       for (int sg = sg_begin; sg < sg_end; ++sg) {
-        const int ws_ = sg % p.segs_w, h = (sg / p.segs_w) % p.H, b = sg / (p.segs_w * p.H);
-        const int w0 = ws_ * p.TW;
+        const int w0 = ws_ * p.TW, h = hg * p.R;          // boxes of R rows: rows past H are zero-filled on both sides
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::stage;
+        uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
         mbar_expect_tx(&full_bar[stage], tx);
         tma_load_4d(sa, &mapA, &full_bar[stage], m_tile * 128, w0, h, b);
         tma_load_4d(sa + atomA, &mapA, &full_bar[stage], m_tile * 128 + 64, w0, h, b);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(sa + Cfg::stageA + j * atomB, &mapB, &full_bar[stage], n_tile * BN + j * 64, w0 - 1, h + dy - 1, b);
+          tma_load_4d(sa + stageA + j * atomB, &mapB, &full_bar[stage], n_tile * BN + j * 64, w0 - 1, h + dy - 1, b);
         if (++stage == S) { stage = 0; phase ^= 1; }
+        if (++ws_ == p.segs_w) { ws_ = 0; if (++hg == p.hgroups) { hg = 0; ++b; } }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {                  // one thread owns the whole MMA stream; descriptors advance incrementally
-      constexpr uint32_t idesc = make_idesc(BN, 1, 1);
-      constexpr uint32_t idesc3 = make_idesc(192, 1, 1);
-      const int kslices = p.TW >> 4;
       const uint64_t a_first = make_sdesc(smem_u32(smem), atomA, 1024);
       // BN == 64: ONE N=192 MMA covers the three dx taps: the N-side "atoms" are the same 64-channel box at a stride
       // (LBO) of one pixel row, i.e. atom j IS the view shifted by j pixels.  The M-side operand is then read from
       // shared memory once instead of three times (an N=64 MMA is bound by that read: 48 cycles instead of 32).
-      const uint64_t b_first = make_sdesc(smem_u32(smem) + Cfg::stageA, BN == 64 ? 128u : atomB, 1024);
-      constexpr uint64_t kStrideD = (uint64_t)Cfg::stage >> 4;
-      uint64_t a_cur = a_first, b_cur = b_first;
-      int stage = 0; uint32_t phase = 0;
-      for (int sg = sg_begin; sg < sg_end; ++sg) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if constexpr (BN == 64) {
-          for (int k = 0; k < kslices; ++k)          // 16 pixel rows = 2 KB per K slice
-            tc_mma_bf16(tmem_base, a_cur + (uint64_t)(k * 128), b_cur + (uint64_t)(k * 128), idesc3, (sg > sg_begin) || (k > 0));
-        } else {
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx)
-            for (int k = 0; k < kslices; ++k)        // dx shifts the N-side view by one pixel row (128 B)
-              tc_mma_bf16(tmem_base + dx * BN, a_cur + (uint64_t)(k * 128), b_cur + (uint64_t)(dx * 8 + k * 128), idesc, (sg > sg_begin) || (k > 0));
-        }
-        tc_commit(&empty_bar[stage]);
-        a_cur += kStrideD; b_cur += kStrideD;
-        if (++stage == S) { stage = 0; phase ^= 1; a_cur = a_first; b_cur = b_first; }
+      const uint64_t b_first = make_sdesc(smem_u32(smem) + stageA, BN == 64 ? 128u : atomB, 1024);
+      switch (p.TW >> 4) {              // K slices per image row: compile-time, so the MMAs of a row are straight-line code
+        case 1: wg_row_mma_loop<BN, 1>(p, tmem_base, full_bar, empty_bar, a_first, b_first, sg_begin, sg_end); break;
+        case 2: wg_row_mma_loop<BN, 2>(p, tmem_base, full_bar, empty_bar, a_first, b_first, sg_begin, sg_end); break;
+        case 3: wg_row_mma_loop<BN, 3>(p, tmem_base, full_bar, empty_bar, a_first, b_first, sg_begin, sg_end); break;
+        default: wg_row_mma_loop<BN, 4>(p, tmem_base, full_bar, empty_bar, a_first, b_first, sg_begin, sg_end); break;
       }
       tc_commit(tfull_bar);
     }
@@ -804,6 +861,58 @@ static int resb_mode() {      // USTRUN_TC_RESB=0 disables the resident-weights 
 }
 constexpr uint32_t kMaxDynSmem = 232448;       // 227 KB opt-in limit per CTA on sm_100
 
+static int ctas_per_n_tile(int n_tiles, int m_tiles) {
+  int per = num_sms() / n_tiles;
+  if (per < 1) per = 1;
+  if (per > m_tiles) per = m_tiles;
+  if (per > USTRUN_MAX_PARTS) per = USTRUN_MAX_PARTS;
+  return per;
+}
+
+// Tiling of the GEMM-row pixel grid and the N tile width.  Default: one TW x TH box of <= 128 pixels per M tile and
+// the widest N tile that divides Cout.  Two things cost whole rounds of the persistent CTAs on small feature maps
+// (the 24 x 24 bottleneck of a 384 x 384 input: 24x5 boxes, the fifth box of an image 80 % full, 40 tiles on the
+// 37 CTAs of an N tile = two rounds for 1.08 rounds of work): (a) badly filled boxes -- an M tile can instead be
+// built from two independent 64-pixel boxes (8x8 covers 24x24 exactly: 36 full tiles, one round); (b) too few tiles
+// per N tile -- a narrower N tile doubles the CTAs that have work.  Cost model: rounds x relative time of one tile
+// (N=128 tiles run at ~1000 vs ~1350 TFLOP/s for N=256, profiles/r01_kernel_microbench_cfg2.txt).
+static int tile_plan_mode() {      // USTRUN_TC_TILEPLAN=0: always one box per tile, widest N tile (A/B comparisons)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USTRUN_TC_TILEPLAN");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+static int plan_fwd_tiles(TcConvParams& p, int B, int H, int W, int Cout) {
+  const int bn_default = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  int tw1, th1, tw2, th2;
+  pick_tile(H, W, 128, false, tw1, th1);
+  pick_tile(H, W, 64, false, tw2, th2);
+  const int units1 = B * ((W + tw1 - 1) / tw1) * ((H + th1 - 1) / th1);
+  const int units2 = B * ((W + tw2 - 1) / tw2) * ((H + th2 - 1) / th2);
+  int best_bn = bn_default, best_halves = 1;
+  double best = 1e30;
+  for (int bn = bn_default; bn >= (bn_default == 256 ? 128 : bn_default); bn >>= 1) {
+    const double tile_cost = bn == 256 ? 1.0 : (bn == 128 ? 0.66 : 0.45);
+    for (int halves = 1; halves <= 2; ++halves) {
+      const int m_tiles = halves == 1 ? units1 : (units2 + 1) / 2;
+      const int per = ctas_per_n_tile(Cout / bn, m_tiles);
+      const double cost = (double)((m_tiles + per - 1) / per) * tile_cost;
+      if (cost < best * 0.97) { best = cost; best_bn = bn; best_halves = halves; }      // earlier candidates win near-ties
+    }
+    if (tile_plan_mode() <= 0) break;
+  }
+  if (tile_plan_mode() <= 0) { best_bn = bn_default; best_halves = 1; }
+  p.halves = best_halves;
+  p.TW = best_halves == 1 ? tw1 : tw2;
+  p.TH = best_halves == 1 ? th1 : th2;
+  p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
+  p.units = B * p.tiles_w * p.tiles_h;
+  p.m_tiles = (p.units + best_halves - 1) / best_halves;
+  return best_bn;
+}
+
 template <int BN, bool ROW, bool RESB>
 static int launch_fwd_impl(const ActView* a, int nmaps, const void* w, long long Ktot, const ActView& out, TcConvParams p, uint32_t smem_bytes,
                            cudaStream_t st) {
@@ -832,11 +941,9 @@ template <int BN, bool ROW = false>
 static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot, const ActView& out, TcConvParams p, cudaStream_t st) {
   using Cfg = FwdCfg<BN, ROW>;
   p.n_tiles = p.Cout / BN;
-  int per = num_sms() / p.n_tiles;
-  if (per < 1) per = 1;
-  if (per > p.m_tiles) per = p.m_tiles;
-  if (per > USTRUN_MAX_PARTS) per = USTRUN_MAX_PARTS;
+  const int per = ctas_per_n_tile(p.n_tiles, p.m_tiles);
   p.ctas_per_n = per;
+  if (p.halves < 1) { p.halves = 1; p.units = p.m_tiles; }
   if constexpr (BN <= 128) {
     // resident weights: the N tile's whole [BN][Ktot] block stays in shared memory, the ring carries activations only
     const long long wres = Ktot * BN * 2;
@@ -867,22 +974,22 @@ int tc_conv_fwd(const void* x, int ldx, const void* w, const float* bias, void* 
   TcConvParams p{};
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.ntaps = ksize * ksize; p.tap_mode = ksize == 3 ? TAP_CONV3 : TAP_NONE;
-  const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   // row mode: 3x3, N tile <= 128 (the L2-bound layers at the top of the UNet), rows that split into whole
   // 128-pixel segments (measured on B200: 64->64 @384 222 -> 155 us; with a 75 %-filled last segment it loses)
   const bool row = row_mode() > 0 && ksize == 3 && BN <= 128 && W % 128 == 0;
-  if (row) { p.TW = 128; p.TH = 1; }
-  else pick_tile(H, W, 128, false, p.TW, p.TH);
-  p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
-  p.m_tiles = B * p.tiles_w * p.tiles_h;
+  if (row) {
+    p.TW = 128; p.TH = 1;
+    p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
+    p.m_tiles = B * p.tiles_w * p.tiles_h;
+    p.halves = 1; p.units = p.m_tiles;
+  } else {
+    BN = plan_fwd_tiles(p, B, H, W, Cout);
+  }
   p.partials = partials; p.bias = bias;
   ActView a{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
   ActView o{y, Cout, W, H, B, ldy, (long long)W * ldy, (long long)H * W * ldy};
-  int nt = Cout / BN, per = num_sms() / nt;
-  if (per < 1) per = 1;
-  if (per > p.m_tiles) per = p.m_tiles;
-  if (per > USTRUN_MAX_PARTS) per = USTRUN_MAX_PARTS;
-  if (nparts_host) *nparts_host = per;
+  if (nparts_host) *nparts_host = ctas_per_n_tile(Cout / BN, p.m_tiles);
   long long Ktot = (long long)p.ntaps * Cin;
   if (row) {
     ActView aa[2] = {a, a};
@@ -901,15 +1008,12 @@ int tc_convT_fwd(const void* x, int ldx, const void* wf, const float* bias, void
   for (int ij = 0; ij < 4; ++ij) {
     TcConvParams p{};
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ntaps = 1; p.tap_mode = TAP_NONE;
-    pick_tile(H, W, 128, false, p.TW, p.TH);
-    p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
-    p.m_tiles = B * p.tiles_w * p.tiles_h;
+    const int BN = plan_fwd_tiles(p, B, H, W, Cout);
     p.partials = nullptr; p.bias = bias;
     ActView a{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
     const char* ybase = (const char*)y + ((long long)(ij >> 1) * 2 * W + (ij & 1)) * ldy * 2;
     ActView o{ybase, Cout, W, H, B, 2LL * ldy, 4LL * W * ldy, 4LL * H * W * ldy};
     const char* wij = (const char*)wf + (size_t)ij * Cout * Cin * 2;
-    const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
     int rc = BN == 256 ? launch_fwd<256>(&a, 1, wij, Cin, o, p, st) : (BN == 128 ? launch_fwd<128>(&a, 1, wij, Cin, o, p, st) : launch_fwd<64>(&a, 1, wij, Cin, o, p, st));
     if (rc) return rc;
   }
@@ -921,16 +1025,13 @@ int tc_convT_dgrad(const void* dy, int lddy, const void* wd, void* dx, int lddx,
   if (Cin % 64 || Cout % 64 || lddy % 8 || lddx % 8) { set_error("tcgen05 convT dgrad needs Cin, Cout %% 64 == 0"); return USTRUN_ERR_ARG; }
   TcConvParams p{};
   p.B = B; p.H = H; p.W = W; p.Cin = Cout; p.Cout = Cin; p.ntaps = 4; p.tap_mode = TAP_PERMAP;
-  pick_tile(H, W, 128, false, p.TW, p.TH);
-  p.tiles_w = (W + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
-  p.m_tiles = B * p.tiles_w * p.tiles_h;
+  const int BN = plan_fwd_tiles(p, B, H, W, Cin);
   ActView a[4];
   for (int ij = 0; ij < 4; ++ij) {
     const char* base = (const char*)dy + ((long long)(ij >> 1) * 2 * W + (ij & 1)) * lddy * 2;
     a[ij] = ActView{base, Cout, W, H, B, 2LL * lddy, 4LL * W * lddy, 4LL * H * W * lddy};
   }
   ActView o{dx, Cin, W, H, B, lddx, (long long)W * lddx, (long long)H * W * lddx};
-  const int BN = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
   long long Ktot = 4LL * Cout;
   if (BN == 256) return launch_fwd<256>(a, 4, wd, Ktot, o, p, st);
   if (BN == 128) return launch_fwd<128>(a, 4, wd, Ktot, o, p, st);
@@ -1009,7 +1110,7 @@ static int wgrad_row_mode() {      // USTRUN_TC_WGRAD_ROW=0 falls back to the on
   }
   return v;
 }
-struct WgRowPlan { bool ok; int swap, Mo, Nn, BN, TW, segs_w, nsegs, m_tiles, n_tiles, splits, sps; };
+struct WgRowPlan { bool ok; int swap, Mo, Nn, BN, TW, R, hgroups, segs_w, nsegs, m_tiles, n_tiles, splits, sps; };
 static WgRowPlan plan_wgrad_row(int B, int H, int W, int Cin, int Cout, int ksize) {
   WgRowPlan g{};
   g.ok = false;
@@ -1021,7 +1122,12 @@ static WgRowPlan plan_wgrad_row(int B, int H, int W, int Cin, int Cout, int ksiz
   if (!TW) return g;
   g.TW = TW;
   g.segs_w = (W + TW - 1) / TW;
-  g.nsegs = B * H * g.segs_w;
+  // narrow feature maps (W <= 32): a 16/32-pixel segment is only 1-2 K slices per tap, and the pipeline is then bound by
+  // TMA/barrier latency, not the tensor pipe -- put R image rows (R * TW <= 64 pixels) into one stage
+  g.R = (tile_plan_mode() > 0 && TW <= 32) ? 64 / TW : 1;
+  if (g.R > H) g.R = H;
+  g.hgroups = (H + g.R - 1) / g.R;
+  g.nsegs = B * g.hgroups * g.segs_w;
   // M side = the unshifted tensor.  Default: dy (Cout rows).  With Cout == 64 < Cin the operands swap so that
   // no half of the 128-row MMA is idle: M side = x (Cin rows), N side = dy shifted by -(tap).
   g.swap = (Cout == 64 && Cin >= 128) ? 1 : 0;
@@ -1036,6 +1142,21 @@ static WgRowPlan plan_wgrad_row(int B, int H, int W, int Cin, int Cout, int ksiz
   long long maxs = (g.nsegs + 15) / 16;                              // >= 16 segments per split
   if (maxs < 1) maxs = 1;
   if (want > maxs) want = maxs;
+  if (tile_plan_mode() > 0 && (items * want > num_sms() || items * want * 5 < (long long)num_sms() * 4)) {
+    // 96 or 192 work items on 148 SMs (the 512/1024-channel layers) leave a third of the SMs idle or cost a second,
+    // mostly empty wave: more K splits even the waves out.  Cost = waves x (K time per split) + the extra passes of
+    // the split-K reduction over the fp32 partials (~5 TB/s).
+    const double t_item = (double)g.nsegs * g.R * 3.0 * (TW / 16) * (g.BN == 128 ? 64.0 : 48.0) * 1.3 / 1900.0;     // us
+    const double t_red = (double)g.Mo * 9.0 * g.Nn * 4.0 * 2.0 / 5.0e6;                                       // us per split
+    double best = 1e30;
+    long long best_s = want;
+    for (long long sct = want; sct <= maxs && sct <= want * 4; ++sct) {
+      const long long waves = (items * sct + num_sms() - 1) / num_sms();
+      const double cost = (double)waves * t_item / (double)sct + t_red * (double)sct;
+      if (cost < best * 0.97) { best = cost; best_s = sct; }
+    }
+    want = best_s;
+  }
   g.sps = (int)((g.nsegs + want - 1) / want);
   g.splits = (g.nsegs + g.sps - 1) / g.sps;
   g.ok = true;
@@ -1046,18 +1167,20 @@ template <int BN>
 static int launch_wgrad_row(const ActView& a, const ActView& b, const WgRowPlan& g, TcWgradRowParams p, cudaStream_t st) {
   using Cfg = WgRowCfg<BN>;
   CUtensorMap mA, mB;
-  int rc = make_act_map(&mA, a.base, a.C, a.W, a.H, a.B, a.sw, a.sh, a.sb, g.TW, 1);
+  int rc = make_act_map(&mA, a.base, a.C, a.W, a.H, a.B, a.sw, a.sh, a.sb, g.TW, g.R);
   if (rc) return rc;
-  rc = make_act_map(&mB, b.base, b.C, b.W, b.H, b.B, b.sw, b.sh, b.sb, g.TW + 8, 1);
+  rc = make_act_map(&mB, b.base, b.C, b.W, b.H, b.B, b.sw, b.sh, b.sb, g.TW + 8, g.R);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad_row<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem);
+    cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad_row<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_tc_wgrad_row<%d>): %s", BN, cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
+  p.nstages = Cfg::stages(g.TW, g.R);
+  p.stage_bytes = Cfg::stage_bytes(g.TW, g.R);
   const int grid = 3 * g.m_tiles * g.n_tiles * g.splits;
-  k_tc_wgrad_row<BN><<<grid, 256, Cfg::smem, st>>>(mA, mB, p);
+  k_tc_wgrad_row<BN><<<grid, 256, Cfg::smem(g.TW, g.R), st>>>(mA, mB, p);
   return check_launch("k_tc_wgrad_row");
 }
 
@@ -1072,6 +1195,7 @@ int tc_conv_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, i
     if (!workspace || ws_bytes < need) { set_error("tc wgrad (row): workspace too small (%lld < %lld)", ws_bytes, need); return USTRUN_ERR_ARG; }
     TcWgradRowParams p{};
     p.B = B; p.H = H; p.W = W; p.Mo = g.Mo; p.Nn = g.Nn; p.TW = g.TW; p.segs_w = g.segs_w; p.nsegs = g.nsegs;
+    p.R = g.R; p.hgroups = g.hgroups;
     p.m_tiles = g.m_tiles; p.n_tiles = g.n_tiles; p.splits = g.splits; p.segs_per_split = g.sps; p.flip = g.swap;
     p.ws = (float*)workspace;
     const ActView& ma = g.swap ? b : a;
