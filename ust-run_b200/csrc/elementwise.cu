@@ -5,6 +5,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ustrun {
@@ -711,7 +713,11 @@ int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const f
   int lanes = 256 / (C / 8);
   int grid = (int)((npix + 4LL * lanes - 1) / (4LL * lanes));       // >= 4 pixels per thread
   if (grid < 1) grid = 1;
-  if (grid > 148 * 6) grid = 148 * 6;                                // two waves of 3 resident blocks per SM
+  // ONE wave of 3 resident blocks per SM: the grid-stride loop takes any number of pixels, and every block is one more
+  // partial row that k_bn_bwd_finalize has to walk (888 rows made that 2-CTA kernel 15 us long, 72 times per step)
+  static int waves = 0;
+  if (!waves) { const char* e = getenv("USTRUN_BN_BWD_WAVES"); waves = e ? atoi(e) : 1; if (waves < 1) waves = 1; }
+  if (grid > 148 * 3 * waves) grid = 148 * 3 * waves;
   *nparts_host = grid;
   DISPATCH_DTYPE(dtype, (k_bn_bwd_reduce<T><<<grid, 256, 256 * 8 * sizeof(float), (cudaStream_t)stream>>>(
                             (const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale, shift, act, npix, C, partials)));
