@@ -61,6 +61,12 @@ int ustrun_conv_wgrad(int impl, const void* dy, int lddy, const void* x, int ldx
                       int dtype, int B, int H, int W, int Cin, int Cout, int ksize, void* workspace,
                       long long workspace_bytes, void* stream);
 long long ustrun_conv_wgrad_workspace_bytes(int impl, int B, int H, int W, int Cin, int Cout, int ksize);
+/* Host-side launch plan of the tcgen05 kernels for a shape (no launch; for tests and tools).
+ * what == 0: forward/dgrad tiling -> out8 = {N tile, row mode, 64-pixel boxes per M tile (1|2), TW, TH, M tiles,
+ *            CTAs per N tile (= BatchNorm partial rows), N tiles};
+ * what == 1: row-mode weight gradient -> out8 = {usable, operands swapped, N tile, TW, image rows per stage, K segments,
+ *            K splits, work items per split}. */
+int ustrun_tc_plan_query(int what, int B, int H, int W, int Cin, int Cout, int ksize, int* out8);
 /* nn.ConvTranspose2d(k2,s2)+bias: unet_parts.py:53,57.  x is [B,H,W,Cin]; y is [B,2H,2W,Cout]. */
 int ustrun_convT2x2_fwd(int impl, const void* x, int ldx, const void* wf, const float* bias, void* y, int ldy,
                         int dtype, int B, int H, int W, int Cin, int Cout, void* stream);

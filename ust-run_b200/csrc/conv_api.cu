@@ -43,6 +43,7 @@ long long tc_conv_wgrad_ws(int B, int H, int W, int Cin, int Cout, int ksize);
 int tc_convT_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout,
                    void* workspace, long long ws_bytes, cudaStream_t st);
 long long tc_convT_wgrad_ws(int B, int H, int W, int Cin, int Cout);
+int tc_plan_query(int what, int B, int H, int W, int Cin, int Cout, int ksize, int* out);
 }  // namespace ustrun
 
 using namespace ustrun;
@@ -79,6 +80,12 @@ int ustrun_conv_fwd(int impl, const void* x, int ldx, const void* w_packed, cons
   ConvGeom g{B, H, W, Cin, Cout, ksize, 0, -1};
   if (dtype == USTRUN_F32) return simt_conv_launch<float>(x, ldx, w_packed, bias, y, ldy, ynchw, g, partials, nparts_host, st);
   return simt_conv_launch<__nv_bfloat16>(x, ldx, w_packed, bias, y, ldy, ynchw, g, partials, nparts_host, st);
+}
+
+int ustrun_tc_plan_query(int what, int B, int H, int W, int Cin, int Cout, int ksize, int* out8) {
+  USTRUN_REQUIRE(out8 && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % 64 == 0 && Cout % 64 == 0 && (ksize == 1 || ksize == 3),
+                 "tc_plan_query: bad args");
+  return tc_plan_query(what, B, H, W, Cin, Cout, ksize, out8);
 }
 
 long long ustrun_conv_wgrad_workspace_bytes(int impl, int B, int H, int W, int Cin, int Cout, int ksize) {

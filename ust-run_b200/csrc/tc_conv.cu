@@ -1212,6 +1212,35 @@ long long tc_conv_wgrad_ws(int B, int H, int W, int Cin, int Cout, int ksize) {
   return tc_wgrad_ws_bytes(B, H, W, Cout, Cin, ksize * ksize);
 }
 
+// Host-side launch plans, exposed for tests and tools (no launch, no device access beyond the SM count):
+//   what == 0: forward / dgrad tiling of a [B,H,W] pixel grid with Cout output channels
+//              out = {BN, row_mode, boxes_per_tile, TW, TH, m_tiles, ctas_per_n_tile, n_tiles}
+//   what == 1: row-mode weight gradient  out = {ok, swapped, BN, TW, rows_per_stage, segments, splits, work_items}
+int tc_plan_query(int what, int B, int H, int W, int Cin, int Cout, int ksize, int* out) {
+  if (what == 0) {
+    TcConvParams p{};
+    int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    const bool row = row_mode() > 0 && ksize == 3 && BN <= 128 && W % 128 == 0;
+    if (row) {
+      p.TW = 128; p.TH = 1; p.halves = 1;
+      p.m_tiles = B * ((W + 127) / 128) * H;
+    } else {
+      BN = plan_fwd_tiles(p, B, H, W, Cout);
+    }
+    out[0] = BN; out[1] = row ? 1 : 0; out[2] = p.halves; out[3] = p.TW; out[4] = p.TH; out[5] = p.m_tiles;
+    out[6] = ctas_per_n_tile(Cout / BN, p.m_tiles); out[7] = Cout / BN;
+    return 0;
+  }
+  if (what == 1) {
+    WgRowPlan g = plan_wgrad_row(B, H, W, Cin, Cout, ksize);
+    out[0] = g.ok ? 1 : 0; out[1] = g.swap; out[2] = g.BN; out[3] = g.TW; out[4] = g.R; out[5] = g.nsegs; out[6] = g.splits;
+    out[7] = 3 * g.m_tiles * g.n_tiles;
+    return 0;
+  }
+  set_error("tc_plan_query: what must be 0 or 1");
+  return USTRUN_ERR_ARG;
+}
+
 // dW[ci][co][ij] = sum_p x[p][ci] * dy[b,2h+i,2w+j][co]
 int tc_convT_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout,
                    void* workspace, long long ws_bytes, cudaStream_t st) {
