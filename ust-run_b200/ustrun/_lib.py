@@ -84,12 +84,15 @@ lib.ustrun_last_error_string.argtypes = []
 lib.ustrun_conv_wgrad_workspace_bytes.restype = i64
 lib.ustrun_conv_wgrad_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32]
 
+lib.ustrun_tc_plan_query.restype = i32
+lib.ustrun_tc_plan_query.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int)]
+
 lib.ustrun_peer_buffer_bytes.restype = i64
 lib.ustrun_peer_buffer_bytes.argtypes = []
 lib.ustrun_fft_amp_mix_workspace_bytes.restype = i64
 lib.ustrun_fft_amp_mix_workspace_bytes.argtypes = [i32, i32, i32, i32, f64]
 
-EXPORTS = sorted(list(_SIGS) + ["ustrun_last_error_string", "ustrun_conv_wgrad_workspace_bytes", "ustrun_peer_buffer_bytes",
+EXPORTS = sorted(list(_SIGS) + ["ustrun_last_error_string", "ustrun_conv_wgrad_workspace_bytes", "ustrun_tc_plan_query", "ustrun_peer_buffer_bytes",
                                  "ustrun_fft_amp_mix_workspace_bytes"])
 
 
