@@ -5,7 +5,12 @@ train_mnms.py:549-556.  Prediction rule: train.py:295-302.  Dice: utils/metrics.
 dc / jc: ``medpy.metric.binary.dc`` / ``.jc`` (train.py:307-311).  medpy is a third-party dependency of the reference
 that is neither vendored under /root/reference nor installed here (the reference pins no version; current release
 0.5.2), so its published definitions are restated: dc = 2|A & B| / (|A| + |B|) with 0.0 on ZeroDivisionError,
-jc = |A & B| / |A | B| (medpy lets the ZeroDivisionError of an empty union propagate; 0.0 here)."""
+jc = |A & B| / |A | B| (medpy lets the ZeroDivisionError of an empty union propagate; 0.0 here).
+
+Pinning: label encodings, the prediction rule and the per-sample Dice values are checked against the reference's own
+lines / functions (oracle/make_golden.py ``case_eval`` -> tests/golden/eval.npz, re-checked by tests/test_oracle_golden.py).
+The batch-mean Dice agrees to the last bit or one ulp: the reference sums Python floats with ``sum()`` (Neumaier-compensated
+since Python 3.12), this file and the device kernel add sequentially in double.  dc / jc: PARITY UNPINNED (no medpy here)."""
 import numpy as np
 import torch
 

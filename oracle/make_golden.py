@@ -340,6 +340,80 @@ def case_hardness():
     print("hardness: reference == oracle bit-for-bit on 3 modes")
 
 
+def _reference_lines(path, start_pat, stop_pat, after=None, exclusive=False):
+    """Source lines of a reference script from the first line containing ``start_pat`` (searched after the first line
+    containing ``after``; ``exclusive``: from the line after it) up to, not including, the first later line containing
+    ``stop_pat`` -- dedented, unmodified."""
+    import textwrap
+    lines = open(os.path.join(REF, path)).read().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if after in l) if after else 0
+    a = next(i for i in range(i0, len(lines)) if start_pat in lines[i]) + (1 if exclusive else 0)
+    b = next(i for i in range(a + 1, len(lines)) if stop_pat in lines[i])
+    return textwrap.dedent("\n".join(lines[a:b])) + "\n", (a + 1, b)
+
+
+def case_eval():
+    """`test()` of the reference (train.py:279-302, train_mnms.py:549-552,...): its label-encoding and prediction lines,
+    sliced out of the scripts and executed unmodified, plus its Dice functions (utils/metrics.py) vs oracle/eval_ref.py."""
+    from oracle import eval_ref as Ev
+    from oracle import hardness_ref as Hr
+    from utils import metrics as ref_metrics               # reference
+    enc_src, enc_at = _reference_lines("train.py", "mask = sample['label'].cuda()", "output = model(data)", after="def test(", exclusive=True)
+    pred_src, pred_at = _reference_lines("train.py", "dice_loss(output, mask.unsqueeze(1), softmax=softmax", "mask, output = mask.cpu(), output.cpu()",
+                                         after="def test(", exclusive=True)
+    mnms_src, mnms_at = _reference_lines("train_mnms.py", "lb_mask = lb_y[:,...,0].eq(255).float()", "ulb_mask = ulb_y", after="for i_batch")
+    dice_fn = {"fundus": ref_metrics.dice_coeff_2label, "prostate": ref_metrics.dice_coeff, "BUSI": ref_metrics.dice_coeff,
+               "mnms": ref_metrics.dice_coeff_3label}           # train.py:220, train_mnms.py:212
+
+    class _Args:
+        dataset = None
+
+    g = torch.Generator().manual_seed(SEED + 21)
+    fx = {"src/encode_lines": np.asarray(enc_at), "src/predict_lines": np.asarray(pred_at), "src/mnms_lines": np.asarray(mnms_at)}
+    for ds, k in (("fundus", 2), ("prostate", 2), ("BUSI", 2), ("mnms", 4)):
+        B, H, W = 3, 24, 20
+        if ds == "mnms":
+            plane = torch.randint(0, 4, (B, H, W), generator=g)
+            raw = torch.stack([(plane == c).to(torch.uint8) * 255 for c in (1, 2, 3)], dim=-1)         # RGB-coded label image
+            ns = {"lb_y": raw.clone(), "torch": torch}
+            exec(compile(mnms_src, "train_mnms.py", "exec"), ns)
+            mask = ns["lb_mask"]
+        else:
+            raw = torch.tensor([0, 128, 255], dtype=torch.uint8)[torch.randint(0, 3, (B, H, W), generator=g)]
+            a = _Args(); a.dataset = ds
+            ns = {"mask": raw.clone(), "args": a, "torch": torch}
+            exec(compile(enc_src, "train.py", "exec"), ns)
+            mask = ns["mask"]
+        output = torch.randn(B, k, H, W, generator=g) * 2
+        if ds == "fundus":
+            output[0] = -5.0                                  # an empty prediction for both structures
+        if ds == "mnms":
+            pred_label = torch.max(torch.softmax(output, dim=1), dim=1)[1]                                 # train_mnms.py:284
+        else:
+            a = _Args(); a.dataset = ds
+            ns = {"output": output.clone(), "mask": mask.clone(), "args": a, "torch": torch}
+            exec(compile(pred_src, "train.py", "exec"), ns)
+            pred_label = ns["pred_label"]
+        dice = dice_fn[ds](np.asarray(pred_label), mask)                                                 # train.py:302
+        per_sample = dice_fn[ds](np.asarray(pred_label), mask, ret_arr=True)
+        # oracle
+        assert torch.equal(Ev.encode_labels(raw, ds), mask), f"eval oracle: label encoding differs ({ds})"
+        assert torch.equal(Ev.predict(output, ds), pred_label), f"eval oracle: prediction differs ({ds})"
+        got_dice, dc, jc = Ev.seg_metrics(pred_label.numpy(), mask.numpy(), ds)
+        mode = {"prostate": "binary", "BUSI": "binary", "fundus": "2label", "mnms": "3label"}[ds]
+        parts = Hr.dice_parts(pred_label.numpy(), mask.numpy(), mode)
+        assert len(parts) == len(per_sample) and all(np.array_equal(a, b) for a, b in zip(parts, per_sample)), f"eval oracle: per-sample dice differs ({ds})"
+        # batch mean: the reference does sum(list of Python floats) / len -- since Python 3.12 that sum is Neumaier-compensated,
+        # so its last bit depends on the interpreter; the oracle (and the device kernel) add sequentially in double
+        assert np.allclose(np.asarray(dice, dtype=np.float64), got_dice, rtol=4e-16, atol=0), f"eval oracle: dice differs ({ds})"
+        fx[f"{ds}/raw"], fx[f"{ds}/mask"], fx[f"{ds}/output"] = raw.numpy(), mask.numpy(), output.numpy()
+        fx[f"{ds}/pred_label"], fx[f"{ds}/dice"] = pred_label.numpy(), np.asarray(dice, dtype=np.float64)
+        fx[f"{ds}/dice_per_sample"] = np.stack(per_sample)
+        fx[f"{ds}/dc"], fx[f"{ds}/jc"] = dc, jc               # medpy restatement (not pinned: medpy is absent here)
+    np.savez_compressed(os.path.join(OUT, "eval.npz"), **fx)
+    print(f"eval: reference lines train.py:{enc_at[0]}-{enc_at[1]}, :{pred_at[0]}-{pred_at[1]}, train_mnms.py:{mnms_at[0]}-{mnms_at[1]} == oracle on 4 datasets")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -349,8 +423,12 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "hardness":
         case_hardness()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":
+        case_eval()
+        return
     case_fft_mix()
     case_hardness()
+    case_eval()
     case_losses()
     case_unet_a(1, 2, 32, 2)
     case_unet_a(3, 3, 32, 2)

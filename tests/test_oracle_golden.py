@@ -171,3 +171,26 @@ def test_hardness_oracle_reproduces_reference_fixture():
         assert np.array_equal(h, fx[f"{mode}/hardness"]) and lq == int(fx[f"{mode}/lq_idx"]), mode
         h1, lq1, _ = Hr.hardness(fx[f"{mode}/stu"], fx[f"{mode}/tea"], mode, first_epoch=True)
         assert np.all(h1 == 1) and lq1 == 0
+
+
+def test_eval_oracle_reproduces_reference_fixture():
+    """oracle/eval_ref.py against tests/golden/eval.npz: label encodings and predictions produced by the reference's own
+    `test()` lines (train.py:279-286, :291-299, train_mnms.py:549-552, sliced out and executed by make_golden) and Dice values
+    of its utils/metrics.py functions.  dc / jc are the medpy restatement (medpy is absent: recorded, not pinned)."""
+    from oracle import eval_ref as Ev
+    from oracle import hardness_ref as Hr
+    fx = np.load(os.path.join(GOLDEN, "eval.npz"))
+    for ds, mode in (("fundus", "2label"), ("prostate", "binary"), ("BUSI", "binary"), ("mnms", "3label")):
+        raw, mask = torch.from_numpy(fx[f"{ds}/raw"]), torch.from_numpy(fx[f"{ds}/mask"])
+        out = torch.from_numpy(fx[f"{ds}/output"])
+        enc = Ev.encode_labels(raw, ds)
+        assert enc.dtype == mask.dtype and torch.equal(enc, mask), ds
+        pred = Ev.predict(out, ds)
+        assert np.array_equal(pred.numpy(), fx[f"{ds}/pred_label"]), ds
+        parts = Hr.dice_parts(pred.numpy(), mask.numpy(), mode)
+        assert np.array_equal(np.stack(parts), fx[f"{ds}/dice_per_sample"]), ds
+        dice, dc, jc = Ev.seg_metrics(pred.numpy(), mask.numpy(), ds)
+        # batch mean: the reference's sum() of Python floats is Neumaier-compensated since Python 3.12 (last-bit differences)
+        assert np.allclose(dice, fx[f"{ds}/dice"], rtol=4e-16, atol=0), ds
+        assert np.array_equal(dc, fx[f"{ds}/dc"]) and np.array_equal(jc, fx[f"{ds}/jc"]), ds
+    assert float(fx["fundus/dice_per_sample"][0, 0]) < 0.05          # the all-background prediction of sample 0
