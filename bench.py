@@ -25,16 +25,21 @@ for _p in (ROOT, os.path.join(ROOT, "ust-run_b200")):
         sys.path.insert(0, _p)
 
 WORKLOADS = {
-    # name: (model, n_channels, n_classes, H, W, B_l, B_u, branch)
-    "cfg1": ("unet_b", 3, 3, 256, 256, 4, 4, "softmax"),
-    "cfg2": ("unet_a", 1, 2, 384, 384, 8, 8, "softmax"),
+    # name: (model, n_channels, n_classes, H, W, B_l, B_u, branch); model suffix "_dsbn3": DomainSpecificBatchNorm2d over 3 domains
+    "cfg1": ("unet_b", 3, 3, 256, 256, 4, 4, "softmax"),                 # BASELINE.json configs[0] (the reference's CPU case)
+    "cfg2": ("unet_a", 1, 2, 384, 384, 8, 8, "softmax"),                 # configs[1]: prostate-shaped, the headline
     "cfg2b": ("unet_b", 1, 2, 384, 384, 8, 8, "softmax"),
-    "cfg3": ("unet_a", 3, 2, 256, 256, 16, 16, "softmax"),
-    "cfg4": ("unet_a", 1, 4, 288, 288, 32, 32, "softmax"),
-    "cfg5": ("unet_a", 3, 2, 512, 512, 64, 64, "softmax"),
+    "cfg3": ("unet_a_dsbn3", 3, 2, 256, 256, 16, 16, "softmax"),         # configs[2]: BUSI-shaped, DSBN over 3 domains (tensor-bound model)
+    "cfg3b": ("unet_b_dsbn3", 3, 2, 256, 256, 16, 16, "softmax"),        # configs[2] on networks/unet.py UNet(norm='dsbn', num_domains=3)
+    "cfg3bn": ("unet_a", 3, 2, 256, 256, 16, 16, "softmax"),             # same shapes, plain BatchNorm (round-1 definition of cfg3)
+    "cfg4": ("unet_a", 1, 4, 288, 288, 32, 32, "softmax"),               # configs[3]: M&Ms-shaped (train_mnms.py)
+    "cfg5": ("unet_a", 3, 2, 512, 512, 64, 64, "softmax"),               # configs[4]
+    "fundus8": ("unet_a", 3, 2, 256, 256, 8, 8, "sigmoid"),              # north_star target: fundus 256x256, 8+8, two sigmoid channels (train.py:404-409,649-657)
+    "fundus8b": ("unet_b", 3, 2, 256, 256, 8, 8, "sigmoid"),
     "tiny": ("unet_a", 1, 2, 64, 64, 2, 2, "softmax"),
 }
 METRIC = "ssl_train_step_images_per_sec"
+DSBN_DOMAINS = (0, 2)          # (labelled batch's domain, unlabelled batch's domain) of the DSBN workloads
 
 
 def peaks():
@@ -90,14 +95,15 @@ class ClockSampler(threading.Thread):
 
 def make_models(model, c, k):
     import torch
-    if model == "unet_a":
+    kw = dict(norm="dsbn", num_domains=3) if model.endswith("_dsbn3") else {}
+    if model.startswith("unet_a"):
         from networks.unet_model import UNet
         torch.manual_seed(1337)
-        student, teacher = UNet(c, k), UNet(c, k)
+        student, teacher = UNet(c, k, **kw), UNet(c, k, **kw)
     else:
         from networks.unet import UNet
         torch.manual_seed(1337)
-        student, teacher = UNet(c, k), UNet(c, k)
+        student, teacher = UNet(c, k, **kw), UNet(c, k, **kw)
     teacher.load_state_dict(student.state_dict())     # teacher = copy of the student after step 0 (alpha=0)
     for p in teacher.parameters():
         p.detach_()
@@ -105,7 +111,7 @@ def make_models(model, c, k):
 
 
 def conv_flops_per_image(model, c, k, H, W):
-    if model == "unet_a":
+    if model.startswith("unet_a"):
         from ustrun.synth import conv_flops_unet_a
         return conv_flops_unet_a(c, k, H, W)
     # UNet-B: trace from the layer table (3 convs per ConvD, conv1/conv2(1x1)/conv3 per ConvU, 3x3 head)
@@ -146,10 +152,12 @@ def run_ours(args):
         from ustrun.dp import DataParallel
         dp = DataParallel(sync_bn=False if args.no_sync_bn else (args.sync_bn if args.sync_bn != "auto" else True))
     model_name, c, k, H, W, Bl, Bu, branch = WORKLOADS[args.workload]
+    dsbn = model_name.endswith("_dsbn3")
     E.set_precision(args.precision)
     student, teacher = make_models(model_name, c, k)
     student, teacher = student.cuda().train(), teacher.cuda().train()
-    trainer = SSLTrainer(student, teacher, n_classes=k, branch=branch, base_lr=0.03, max_iterations=60000, threshold=0.95, dp=dp)
+    use_graph = args.graph == "on" or (args.graph == "auto" and (dp is None or dp.graph_safe) and args.workload != "cfg5")
+    trainer = SSLTrainer(student, teacher, n_classes=k, branch=branch, base_lr=0.03, max_iterations=60000, threshold=0.95, dp=dp, use_graph=use_graph)
     trainer.iter_num = 30000                      # mid-training: consistency weight 1.0, alpha 0.99
     host = S.synthetic_batch(c, k, H, W, Bl, Bu, seed=1337 + rank, branch=branch)
     host["lb_mask"] = host["lb_mask"].to(torch.uint8)
@@ -159,6 +167,7 @@ def run_ours(args):
     host["choice"] = host["choice"].to(torch.int32)
     pinned = {kk: v.contiguous().pin_memory() for kk, v in host.items()}
     dev = {kk: v.cuda() for kk, v in pinned.items()}
+    extra = dict(domain_lb=DSBN_DOMAINS[0], domain_ulb=DSBN_DOMAINS[1]) if dsbn else {}
 
     def sync_all():
         if world > 1:
@@ -180,40 +189,51 @@ def run_ours(args):
         return float(ms) / steps
 
     lq_dev = dev["ulb_w"][:1].contiguous()       # steady state: the batch-1 low-quality forward (train.py:740)
+    lq_pinned = pinned["ulb_w"][:1].contiguous().pin_memory()
 
     def step_resident():
-        trainer.step(dev, lq=lq_dev)
+        return trainer.step({**dev, **extra}, lq=lq_dev)
 
-    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values()) + lq_pinned.numel() * 4
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        d = {kk: v.cuda(non_blocking=True) for kk, v in pinned.items()}
-        out = trainer.step(d, lq=d["ulb_w"][:1])
+        # the public call with HOST (pinned) inputs: graph mode copies them straight into the capture's static buffers
+        if trainer.use_graph:
+            out = trainer.step({**pinned, **extra}, lq=lq_pinned)
+        else:
+            d = {kk: v.cuda(non_blocking=True) for kk, v in pinned.items()}
+            out = trainer.step({**d, **extra}, lq=lq_pinned.cuda(non_blocking=True))
         loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()        # the user reads the loss every step
+        return out
 
-    # one cudaMalloc up front instead of ~40 during the first 20 steps (cfg5 needs > 100 GB of activations + workspaces)
-    pool = E.reserve_pool(fraction=0.6 if args.workload == "cfg5" else 0.5, cap=160 << 30)
-    for _ in range(args.warmup):
+    # one cudaMalloc up front instead of ~40 during the first 20 steps (cfg5 needs > 100 GB of activations + workspaces);
+    # graph mode gives the eager pool back before capturing, so it only needs a small reservation
+    pool = E.reserve_pool(fraction=(0.6 if args.workload == "cfg5" else 0.5) if not use_graph else 0.1, cap=160 << 30)
+    out0 = step_resident()                       # step 0 from the seeded initial weights: kept for the parity record
+    parity_loss0 = out0["loss"].detach().clone()
+    parity_pl0 = out0["pseudo_label"].detach().clone()
+    for _ in range(max(args.warmup, 3 if use_graph else 0) - 1):
         step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    l0 = E.KERNELS
     ms = timed(step_resident, args.steps)
-    launches = E.KERNELS - l0
+    launches = trainer.launches_per_step * args.steps
     if rank == 0:
         sampler.stop()
-    # per-kernel-class roofline: a separate short pass with CUDA events around every conv launch (the events
+    # per-kernel-class roofline: a separate short EAGER pass with CUDA events around every conv launch (the events
     # serialise the weight-gradient side stream, so this pass is not the one that is timed)
     prof_steps = min(args.steps, 3)
+    trainer.use_graph = False
     E.PROFILE_EVENTS = [] if rank == 0 else None
     timed(step_resident, prof_steps)
     prof_events = E.PROFILE_EVENTS
     E.PROFILE_EVENTS = None
-    for _ in range(min(2, args.warmup)):
+    trainer.use_graph = use_graph
+    for _ in range(max(min(3, args.warmup), 3 if use_graph else 1)):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     imgs = world * (Bl + Bu)
@@ -227,7 +247,7 @@ def run_ours(args):
     f_img = conv_flops_per_image(model_name, c, k, H, W)
     # forwards: 3 teacher + S0 + 3 student branches on B_u, 1 on B_l, 1 low-quality image; backward (dgrad+wgrad = 2x) on 4 branches
     step_flops = (7 * Bu + Bl + 1) * f_img + (Bl + 3 * Bu) * 2 * f_img
-    # per-kernel-class roofline from CUDA events recorded around the conv launches in the timed region
+    # per-kernel-class roofline from CUDA events recorded around the conv launches in the profiling pass
     classes = {}
     torch.cuda.synchronize()
     for name, flops, ev0, ev1 in (prof_events or []):
@@ -249,65 +269,133 @@ def run_ours(args):
     conv_layers = {"tflops": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None, "ms_per_step": tc_ms / prof_steps,
                    "frac_of_sustained_peak": tc_flops / (tc_ms * 1e-3) / 1e12 / pk["tf_sustained"] if tc_ms > 0 else None,
                    "frac_of_burst_peak": tc_flops / (tc_ms * 1e-3) / 1e12 / pk["tf_burst"] if tc_ms > 0 else None}
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (tools/ncu_traffic.py)
-    traffic, traffic_note = None, "no capture committed"
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_tc_conv_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic = tj["dram_bytes_per_launch"]
-        traffic_note = (f"mean over {tj['launches']} k_tc_conv launches (13 layers x fwd/dgrad, cfg2 shapes) of dram__bytes_read+write from {tj['source']}; "
-                        f"algorithmic {tj['algorithmic_bytes_per_launch']:.3e} B/launch, ratio {tj['ratio']:.2f}")
+    # DRAM bytes per launch / tensor-pipe activity of the dominant kernel from the committed `ncu --set full` capture (tools/ncu_traffic.py)
+    traffic, traffic_note, tensor_pipe = None, "no capture committed", None
+    for fname in ("r02_ncu_tc_conv_traffic.json", "r01_ncu_tc_conv_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", fname)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes_per_launch"]
+            tensor_pipe = tj.get("tensor_pipe_pct")
+            traffic_note = (f"mean over {tj['launches']} k_tc_conv launches (cfg2 shapes) of dram__bytes_read+write from {tj['source']}; "
+                            f"algorithmic {tj['algorithmic_bytes_per_launch']:.3e} B/launch, ratio {tj['ratio']:.2f}")
+            break
     roofline = {"bound": "tensor", "kernel": top, "achieved": kern[top]["tflops"] if top else None, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (kern[top]["tflops"] / peak_tf) if top else None, "traffic": traffic, "traffic_note": traffic_note,
+                "frac": (kern[top]["tflops"] / peak_tf) if top else None, "traffic": traffic, "traffic_note": traffic_note, "tensor_pipe_pct": tensor_pipe,
                 "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                 "flops_per_launch": (classes[top][0] / classes[top][2]) if top else None,
                 "us_per_launch": (classes[top][1] * 1e3 / classes[top][2]) if top else None,
                 "conv_layers": conv_layers, "hbm_kernels": hbm, "hbm_peak_gbs": pk["hbm_gbs"],
                 "step_conv_tflops": step_flops / (ms * 1e-3) / 1e12, "step_frac_of_peak": step_flops / (ms * 1e-3) / 1e12 / peak_tf,
-                "kernels": kern}
+                "step_frac_of_burst_peak": step_flops / (ms * 1e-3) / 1e12 / pk["tf_burst"], "kernels": kern}
     cpu = cpu_baseline(args, bounded=True)
+    gpu_base, parity = (None, None)
+    if world == 1 and not args.no_gpu_baseline:
+        gpu_base, parity = gpu_baseline(args, float(parity_loss0), parity_pl0)
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"{args.workload}: {model_name} {c}x{H}x{W}, {k} classes, {Bl}+{Bu} per GPU, {branch} branch, SSL step",
                        "global_batch": imgs, "parallelism": f"dp{world}", "l2": "working set (GBs of activations per step) >> 126 MB L2; no flush needed", "pool_reserved_gib": round(pool / 2**30, 1),
+                       "cuda_graph": bool(use_graph), "dsbn_domains": list(DSBN_DOMAINS) if dsbn else None,
                        "sync_bn": (False if (world == 1 or args.no_sync_bn) else ("peer" if dp is not None and dp.peer is not None else "nccl"))},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "parity": parity}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_step_time(model_name, c, k, H, W, B, steps, warmup, branch="softmax"):
+def oracle_models(model_name, c, k, device="cpu"):
+    """State dicts + forward of the oracle port for a workload (same seed => same initial weights as make_models)."""
+    from oracle import unet_ref as U
+    dsbn = model_name.endswith("_dsbn3")
+    kw = dict(norm="dsbn", num_domains=3) if dsbn else {}
+    if model_name.startswith("unet_a"):
+        st = U.init_unet_a(c, k, seed=1337, **kw)
+        fwd = (lambda s, x, dl: U.unet_a_forward(s, x, True, domain_label=dl)) if dsbn else (lambda s, x: U.unet_a_forward(s, x, True))
+    else:
+        st = U.init_unet_b(c, k, seed=1337, **kw)
+        fwd = (lambda s, x, dl: U.unet_b_forward(s, x, True, domain_label=dl)) if dsbn else (lambda s, x: U.unet_b_forward(s, x, True))
+    st = {n: v.to(device) for n, v in st.items()}
+    return st, {n: v.clone() for n, v in st.items()}, fwd, dsbn
+
+
+def oracle_domains(dsbn, B_l, B_u):
+    if not dsbn:
+        return None
+    import torch
+    u, l = torch.full((B_u,), DSBN_DOMAINS[1], dtype=torch.long), torch.full((B_l,), DSBN_DOMAINS[0], dtype=torch.long)
+    return dict(t1=u, t2=u, t3=l, s0=u, lb=l, ul=u, lu=l, s=u, lq=u)
+
+
+def cpu_step_time(model_name, c, k, H, W, Bl, Bu, steps, warmup, branch="softmax"):
     """Time the oracle port (torch CPU fp32 restatement of the reference step) on the host cores."""
     import torch
     from oracle import ssl_step_ref as S
-    from oracle import unet_ref as U
     torch.set_num_threads(os.cpu_count() or 1)
-    if model_name == "unet_a":
-        st_s, st_t = U.init_unet_a(c, k, seed=1337), U.init_unet_a(c, k, seed=1337)
-        fwd = lambda s, x: U.unet_a_forward(s, x, True)
-    else:
-        st_s, st_t = U.init_unet_b(c, k, seed=1337), U.init_unet_b(c, k, seed=1337)
-        fwd = lambda s, x: U.unet_b_forward(s, x, True)
-    batch = S.synthetic_batch(c, k, H, W, B, B, seed=1337, branch=branch)
+    st_s, st_t, fwd, dsbn = oracle_models(model_name, c, k)
+    batch = S.synthetic_batch(c, k, H, W, Bl, Bu, seed=1337, branch=branch)
     bufs, times = {}, []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        S.ssl_step(fwd, st_s, st_t, bufs, batch, n_classes=k, branch=branch, iter_num=30000 + i, max_iterations=60000)
+        S.ssl_step(fwd, st_s, st_t, bufs, batch, n_classes=k, branch=branch, iter_num=30000 + i, max_iterations=60000, lq=batch["ulb_w"][:1],
+                   domains=oracle_domains(dsbn, Bl, Bu))
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return sum(times) / len(times)
+
+
+def gpu_baseline(args, our_loss0, our_pl0):
+    """Baseline leg (N=1 only, like cpu_baseline): the reference's step as PyTorch eager + cuDNN executes it on THIS GPU -- the
+    oracle port moved to CUDA -- in fp32 (TF32 off), bf16 autocast and fp16 autocast (what the reference ships, train.py:30,551).
+    Also yields the parity record: our bf16 step-0 loss / pseudo labels against the fp32 eager step from the same seeded weights
+    and inputs.  The oracle is the yardstick here, never the thing measured as 'ours'."""
+    import torch
+    model_name, c, k, H, W, Bl, Bu, branch = WORKLOADS[args.workload]
+    if (Bl + Bu) * H * W > 16 * 384 * 384 * 2:
+        return {"skipped": "eager autograd of this workload does not fit next to the measured arm's pool (SURVEY H3)"}, None
+    try:
+        from oracle import ssl_step_ref as S
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.benchmark = True
+        torch.cuda.empty_cache()
+        batch = {kk: v.cuda() for kk, v in S.synthetic_batch(c, k, H, W, Bl, Bu, seed=1337, branch=branch).items()}
+        res, parity = {}, None
+        for name, dt, scale in (("fp32", None, 1.0), ("bf16_autocast", torch.bfloat16, 1.0), ("fp16_autocast", torch.float16, 1024.0)):
+            st_s, st_t, fwd, dsbn = oracle_models(model_name, c, k, "cuda")
+            bufs, ts = {}, []
+            for i in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                with torch.autocast("cuda", dtype=dt, enabled=dt is not None):
+                    out = S.ssl_step(fwd, st_s, st_t, bufs, batch, n_classes=k, branch=branch, iter_num=30000 + i, max_iterations=60000, lq=batch["ulb_w"][:1],
+                                     domains=oracle_domains(dsbn, Bl, Bu), loss_scale=scale)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+                if i == 0 and name == "fp32":
+                    ref = float(out["loss"])
+                    agree = float((our_pl0.reshape(-1).long() == out["pseudo_label"].reshape(-1).long()).float().mean())
+                    parity = {"what": "step 0 from the seeded initial weights: ours (" + args.precision + ") vs the oracle port in fp32 on this GPU (cuDNN, TF32 off)",
+                              "loss_ours": our_loss0, "loss_fp32_eager": ref, "loss_rel_err": abs(our_loss0 - ref) / abs(ref), "pseudo_label_agreement": agree,
+                              "full_size_tests": "tests/test_parity_fullsize_gpu.py (warmed weights: logits, gradients, state after the step, 50-step trajectory)"}
+            res[name] = {"ms_per_step": min(ts[1:]) * 1e3, "images_per_s": (Bl + Bu) / min(ts[1:])}
+            del st_s, st_t, bufs, out
+            torch.cuda.empty_cache()
+        res["what"] = "oracle port of the reference step under torch eager + cuDNN on this GPU, best of 2 after 1 warm-up step"
+        return res, parity
+    except Exception as e:
+        return {"failed": f"{type(e).__name__}: {e}"}, None
 
 
 def cpu_baseline(args, bounded=True):
     model_name, c, k, H, W, Bl, Bu, branch = WORKLOADS[args.workload]
     B = 1 if bounded else Bl
     try:
-        t = cpu_step_time(model_name, c, k, H, W, B, steps=1, warmup=0, branch=branch)
+        t = cpu_step_time(model_name, c, k, H, W, B, B, steps=1, warmup=0, branch=branch)
         return {"value": 2 * B / t, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                "sample": f"1 untimed-warmup-free step of the oracle port at B_l=B_u={B} (same {c}x{H}x{W} shape, fp32, {os.cpu_count()} torch threads); "
-                          f"{t:.1f} s; per-image work is batch-independent"}
+                "sample": f"1 step of the oracle port at B_l=B_u={B} (+ the batch-1 low-quality forward; same {c}x{H}x{W} shape, fp32, {os.cpu_count()} torch threads); "
+                          f"{t:.1f} s; bounded sample of the {Bl}+{Bu} step, see --impl reference for the full-size CPU step"}
     except Exception as e:          # never lose the GPU line because the CPU leg failed
         return {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
@@ -315,21 +403,29 @@ def cpu_baseline(args, bounded=True):
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  /root/reference (pure
     Python, no build) does not travel to the GPU box, so this times the oracle port, which is pinned
-    bit-for-bit against the reference modules (tests/test_oracle_golden.py)."""
+    bit-for-bit against the reference modules (tests/test_oracle_golden.py).  Same workload as the measured
+    arm (full B_l + B_u step incl. the batch-1 low-quality forward) whenever 1 warm-up + 2 timed steps fit the
+    time budget (--ref-budget seconds, estimated from a 1+1 probe step); otherwise the largest batch that fits."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     model_name, c, k, H, W, Bl, Bu, branch = WORKLOADS[args.workload]
-    B = 1
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    t = cpu_step_time(model_name, c, k, H, W, B, steps=steps, warmup=warmup, branch=branch)
-    value = 2 * B / t
+    t_probe = cpu_step_time(model_name, c, k, H, W, 1, 1, steps=1, warmup=0, branch=branch)
+    steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
+    per_image = t_probe / 2.0                              # optimistic: larger batches thread better
+    fit = int(args.ref_budget / max(per_image * (steps + warmup), 1e-9)) // 2
+    B_l, B_u = (Bl, Bu) if fit >= max(Bl, Bu) else (max(1, min(Bl, fit)), max(1, min(Bu, fit)))
+    same = (B_l, B_u) == (Bl, Bu)
+    t = cpu_step_time(model_name, c, k, H, W, B_l, B_u, steps=steps, warmup=warmup, branch=branch)
+    value = (B_l + B_u) / t
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    desc = f"{Bl}+{Bu} per step" if same else f"bounded sample {B_l}+{B_u} of the {Bl}+{Bu} step"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {model_name} {c}x{H}x{W}, {k} classes, bounded sample {B}+{B} of the {Bl}+{Bu} step, {branch} branch, SSL step on CPU"},
+            "config": {"workload": f"{args.workload}: {model_name} {c}x{H}x{W}, {k} classes, {desc}, {branch} branch, SSL step on CPU", "same_batch_as_gpu_arm": same,
+                       "global_batch": B_l + B_u},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{steps} step(s) at B_l=B_u={B}, fp32, {os.cpu_count()} torch threads"},
+                             "sample": f"{steps} timed step(s) after {warmup} warm-up at B_l={B_l}, B_u={B_u}, fp32, {os.cpu_count()} torch threads (probe step at 1+1: {t_probe:.1f} s)"},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -345,6 +441,9 @@ def main():
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--sync-bn", default="auto", choices=["auto", "peer", "nccl"], help="cross-rank BN statistics: fused peer-memory kernel or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-cuDNN baseline / parity leg (N=1)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the step as one CUDA graph (auto: single GPU, not cfg5)")
+    ap.add_argument("--ref-budget", type=float, default=420.0, help="--impl reference: seconds of CPU time the whole run may take")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

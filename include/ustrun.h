@@ -204,6 +204,11 @@ typedef struct {
 int ustrun_sgd_ema_multi(const ustrun_param_t* table, const int* blk_tensor, const long long* blk_offset, int nblocks,
                          float lr, float momentum, float weight_decay, float alpha, float grad_scale, int do_sgd,
                          int do_ema, void* stream);
+/* Same update with the per-step scalars read from DEVICE memory: hyper = float[3] {lr, alpha, grad_scale}
+ * (train.py:854-856 poly lr, :91 EMA alpha).  A captured CUDA graph of the step replays with new values
+ * after a 12-byte copy; nothing in the launch arguments changes from step to step. */
+int ustrun_sgd_ema_multi_dev(const ustrun_param_t* table, const int* blk_tensor, const long long* blk_offset, int nblocks,
+                             const float* hyper, float momentum, float weight_decay, int do_sgd, int do_ema, void* stream);
 
 /* ---- frequency-domain style mix -------------------------------------------
  * Replaces the per-sample host loop of train.py:628-636 (extract_amp_spectrum train.py:158-165,

@@ -261,6 +261,153 @@ def case_step(model, branch, n_channels, n_classes, hw, B, iter_num, bank):
     print(f"{name}: loss={loss.item():.6f} mask_mean={comp['mask'].mean().item():.3f} ok")
 
 
+
+# ---- DSBN through the whole UNet-B: the reference modules under a documented run-time patch ----
+# Upstream, ``UNet(norm='dsbn')`` raises TypeError at construction: ConvD/ConvU call ``normalization(planes, norm)``
+# without ``num_domains`` (unet.py:38,82) and their forwards call ``self.bnX(x)`` without ``domain_label``
+# (unet.py:58-70,98-115).  The patch below changes NOTHING in the reference's files; at run time it
+#   (1) wraps ``networks.unet.normalization`` so that the 'dsbn' case receives ``num_domains`` (2 lines), and
+#   (2) gives ``_DomainSpecificBatchNorm.forward`` a default ``domain_label`` taken from a context variable and
+#       makes it return the bare tensor in that case (4 lines) -- the selection rule itself,
+#       ``self.bns[domain_label[0]](x)`` (dsbn.py:26), is the reference's own line.
+# ConvD / ConvU / UNet.forward, the ModuleList of BatchNorm2d and the initialisation then run unmodified.
+class _DsbnPatch:
+    current = [None]
+
+    def __init__(self, num_domains):
+        self.num_domains = num_domains
+
+    def __enter__(self):
+        from networks import dsbn as ref_dsbn
+        self._norm, self._fwd = ref_unet_b.normalization, ref_dsbn._DomainSpecificBatchNorm.forward
+        nd, orig = self.num_domains, self._norm
+        ref_unet_b.normalization = lambda planes, norm='gn', num_domains=None: orig(planes, norm, nd if norm == 'dsbn' else num_domains)
+        orig_fwd, cur = self._fwd, self.current
+
+        def forward(mod, x, domain_label=None):
+            if domain_label is not None:
+                return orig_fwd(mod, x, domain_label)
+            return orig_fwd(mod, x, cur[0])[0]
+        ref_dsbn._DomainSpecificBatchNorm.forward = forward
+        return self
+
+    def __exit__(self, *exc):
+        from networks import dsbn as ref_dsbn
+        ref_unet_b.normalization, ref_dsbn._DomainSpecificBatchNorm.forward = self._norm, self._fwd
+
+
+class _WithDomain(torch.nn.Module):
+    """Calls the patched reference network with the context variable set (keeps run_model_case generic)."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def forward(self, x, domain_label=None):
+        _DsbnPatch.current[0] = domain_label
+        return self.net(x)
+
+    def state_dict(self, *a, **k):
+        return self.net.state_dict(*a, **k)
+
+    def named_parameters(self, *a, **k):
+        return self.net.named_parameters(*a, **k)
+
+
+def case_unet_b_dsbn(n_channels=3, n_classes=2, hw=32, batch=2, domains=3):
+    with _DsbnPatch(domains):
+        torch.manual_seed(SEED)
+        ref = ref_unet_b.UNet(n_channels=n_channels, n_classes=n_classes, norm="dsbn")
+        st = U.init_unet_b(n_channels, n_classes, seed=SEED, norm="dsbn", num_domains=domains)
+        assert_same_state(ref, st)
+        x = torch.rand(batch, n_channels, hw, hw, generator=torch.Generator().manual_seed(SEED + 4)) * 2 - 1
+        dl = torch.tensor([1, 2][:batch])
+        run_model_case(f"unet_b_dsbn{domains}_c{n_channels}_k{n_classes}_{hw}", _WithDomain(ref), st,
+                       lambda s, t: U.unet_b_forward(s, t, True, domain_label=dl), x, n_classes, extra={"domain_label": dl})
+
+
+STEP_DOMAIN_TAGS = ("t1", "t2", "t3", "s0", "lb", "ul", "lu", "s")
+
+
+def step_domains(d_lb, d_ulb, B):
+    """Domain of each forward of the step (this repo's convention; upstream has no DSBN step): a forward belongs to
+    the domain of the image that fills the area OUTSIDE the CutMix box -- t1/t2/s0/ul/s: the unlabelled batch's
+    domain, t3/lb/lu: the labelled batch's."""
+    u, l = torch.full((B,), d_ulb, dtype=torch.long), torch.full((B,), d_lb, dtype=torch.long)
+    return dict(t1=u, t2=u, t3=l, s0=u, lb=l, ul=u, lu=l, s=u, lq=u)
+
+
+def case_step_dsbn(n_channels=3, n_classes=2, hw=32, B=2, iter_num=3000, domains=3, d_lb=0, d_ulb=2):
+    """Whole DSBN step: patched reference UNet-B modules + reference loss + torch SGD vs the restated oracle."""
+    branch, thr = "softmax", 0.6
+    with _DsbnPatch(domains):
+        torch.manual_seed(SEED)
+        ref_s = ref_unet_b.UNet(n_channels, n_classes, norm="dsbn")
+        ref_t = ref_unet_b.UNet(n_channels, n_classes, norm="dsbn")
+        torch.manual_seed(SEED)
+        st_s = U.init_unet_b(n_channels, n_classes, norm="dsbn", num_domains=domains)
+        st_t = U.init_unet_b(n_channels, n_classes, norm="dsbn", num_domains=domains)
+        for p in ref_t.parameters():
+            p.detach_()
+        assert_same_state(ref_s, st_s), assert_same_state(ref_t, st_t)
+        batch = S.synthetic_batch(n_channels, n_classes, hw, hw, B, B, seed=SEED, branch=branch)
+        dom = step_domains(d_lb, d_ulb, B)
+        ref_s.train(), ref_t.train()
+        opt = torch.optim.SGD(ref_s.parameters(), lr=0.03, momentum=0.9, weight_decay=0.0001)
+        dice = ref_losses.DiceLossWithMask(n_classes)
+        ce = torch.nn.CrossEntropyLoss(reduction="none")
+        b = batch
+        img_box = b["box"].unsqueeze(1)
+        mix_img = b["cut_img"][b["choice"]]
+
+        def run(net, x, tag):
+            _DsbnPatch.current[0] = dom[tag]
+            return net(x)
+        with torch.no_grad():
+            t1 = run(ref_t, b["ulb_w"], "t1"); t2 = run(ref_t, S.mix(b["ulb_w"], mix_img, img_box), "t2"); t3 = run(ref_t, S.mix(mix_img, b["ulb_w"], img_box), "t3")
+            comp = S.compose(t1, t2, t3, b["box"], b["cut_label"], b["cut_mask"], b["choice"], thr, branch)
+        run(ref_s, b["ulb_w"], "s0")
+        outs = [run(ref_s, b["lb_x"], "lb"), run(ref_s, S.mix(b["ulb_s"], b["move_transx"], img_box), "ul"),
+                run(ref_s, S.mix(b["move_transx"], b["ulb_s"], img_box), "lu"), run(ref_s, b["ulb_s"], "s")]
+        tg = [(b["lb_mask"], None), (comp["pseudo_label_ul"], comp["mask_ul"]), (comp["pseudo_label_lu"], comp["mask_lu"]), (comp["pseudo_label_w"], comp["mask_w"])]
+        terms = []
+        for o, (t, m) in zip(outs, tg):
+            c = ce(o, t)
+            if m is not None:
+                c = c * m.squeeze(1)
+            terms.append(c.mean() + dice(o, t.unsqueeze(1), mask=m, softmax=True))
+        cw = 1.0 * ref_ramps.sigmoid_rampup(iter_num // (30000 / 200.0), 200.0)
+        loss = terms[0] + cw * (terms[1] + terms[2] + cw * terms[3])
+        opt.zero_grad(); loss.backward(); opt.step()
+        alpha = min(1 - 1 / (iter_num + 1), 0.99)
+        for ep, p in zip(ref_t.parameters(), ref_s.parameters()):
+            ep.data.mul_(alpha).add_(p.data, alpha=1 - alpha)
+        # only the BatchNorms of the two domains in play received gradients (SGD skips grad=None: no weight decay either)
+        for n_, p in ref_s.named_parameters():
+            if ".bns." in n_:
+                d = int(n_.split(".bns.")[1].split(".")[0])
+                assert (p.grad is not None) == (d in (d_lb, d_ulb)), n_
+        out = S.ssl_step(lambda s, x, dl: U.unet_b_forward(s, x, True, domain_label=dl), st_s, st_t, {}, batch, n_classes=n_classes, branch=branch,
+                         iter_num=iter_num, max_iterations=30000, lr=0.03, threshold=thr, domains=dom)
+        assert torch.equal(out["loss"], loss.detach()), (out["loss"], loss)
+        assert_same_state(ref_s, {k: v.detach() for k, v in st_s.items()})
+        assert_same_state(ref_t, {k: v.detach() for k, v in st_t.items()})
+    name = f"dsbnstep_b_{branch}_c{n_channels}_k{n_classes}_{hw}_b{B}_it{iter_num}_d{d_lb}{d_ulb}of{domains}"
+    fx = {"loss": np_(loss), "terms": np.array([t.item() for t in terms]), "cw": np.float64(cw), "threshold": np.float64(thr),
+          "d_lb": np.int64(d_lb), "d_ulb": np.int64(d_ulb), "domains": np.int64(domains)}
+    for k, v in comp.items():
+        fx["comp/" + k] = np_(v).astype(np.uint8)
+    for k, v in out["logits"].items():
+        fx["logits/" + k] = np_(v)
+    for k, v in digest(ref_s.state_dict()).items():
+        fx["student_after/" + k] = v
+    for k, v in digest(ref_t.state_dict()).items():
+        fx["teacher_after/" + k] = v
+    fx["no_grad_params"] = np.array([k for k, v in out["grads"].items() if v is None])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+    print(f"{name}: loss={loss.item():.6f} ok")
+
+
 def _reference_fft_functions():
     """train.py cannot be imported (argparse + dataset dispatch at import time), so the three FFT
     helpers are lifted out of its source with ``ast`` at generation time and executed unmodified; only
@@ -426,6 +573,10 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "eval":
         case_eval()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "dsbn":
+        case_unet_b_dsbn()
+        case_step_dsbn()
+        return
     case_fft_mix()
     case_hardness()
     case_eval()
@@ -435,6 +586,8 @@ def main():
     case_unet_b(3, 3, 32, 2)
     case_unet_b(1, 2, 48, 2)
     case_dsbn()
+    case_unet_b_dsbn()
+    case_step_dsbn()
     case_step("a", "softmax", 1, 2, 32, 2, iter_num=0, bank=0)
     case_step("a", "softmax", 1, 4, 32, 2, iter_num=15000, bank=2)
     case_step("b", "softmax", 3, 3, 32, 2, iter_num=3000, bank=0)

@@ -177,7 +177,7 @@ def ema_update(teacher_params, student_params, alpha):
 def ssl_step(forward, student, teacher, bufs, batch, *, n_classes, branch="softmax", iter_num=0,
              max_iterations=30000, lr=0.03, base_lr=0.03, threshold=0.95, consistency=1.0,
              consistency_rampup=200.0, ema_decay=0.99, momentum=0.9, weight_decay=1e-4,
-             lq=None, update=True):
+             lq=None, update=True, domains=None, loss_scale=1.0):
     """One step.  ``forward(state, x) -> logits`` runs a train-mode forward with BN side effects on
     ``state`` (a flat dict holding params *and* buffers).  ``student``/``teacher`` are such dicts,
     ``bufs`` the SGD momentum buffers (dict name -> tensor|None).
@@ -185,9 +185,17 @@ def ssl_step(forward, student, teacher, bufs, batch, *, n_classes, branch="softm
     batch keys: lb_x, lb_mask, ulb_w, ulb_s, move_transx, box [Bu,H,W], choice (LongTensor [Bu]),
     cut_img, cut_label, cut_mask.  ``lq`` (optional) = the batch-1 low-quality image whose forward
     only updates the student's BN running statistics (train.py:740).
+    ``domains`` (DSBN networks only, not upstream): dict forward tag -> ``domain_label`` tensor; ``forward`` is then
+    called as ``forward(state, x, domain_label)``.  Tags in call order: t1 t2 t3 (teacher), s0, lb, ul, lu, s, lq.
+    ``loss_scale``: static GradScaler factor (train.py:551,842-845): the scaled loss is back-propagated and the
+    gradients are unscaled before SGD -- a no-op in exact arithmetic, needed for the fp16-autocast yardstick.
     Returns a dict of losses / compositions / grads; mutates student, teacher, bufs if ``update``."""
     from .unet_ref import split_state
     b = batch
+    if domains is not None:
+        fwd0 = forward
+        order = iter(("t1", "t2", "t3", "s0", "lb", "ul", "lu", "s", "lq"))
+        forward = lambda state, x: fwd0(state, x, domains[next(order)])
     img_box = b["box"].unsqueeze(1)
     mix_img = b["cut_img"][b["choice"]]
     with torch.no_grad():                                                                 # :638-647
@@ -215,8 +223,9 @@ def ssl_step(forward, student, teacher, bufs, batch, *, n_classes, branch="softm
     lu = masked_term(l_lu, comp["pseudo_label_lu"], comp["mask_lu"], n_classes, branch)
     s = masked_term(l_s, comp["pseudo_label_w"], comp["mask_w"], n_classes, branch)
     loss = sup + cw * (ul + lu + cw * s)                                                  # :838
-    loss.backward()
-    grads = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in params.items()}
+    (loss * loss_scale if loss_scale != 1.0 else loss).backward()
+    inv = 1.0 / loss_scale
+    grads = {k: ((p.grad.detach().clone() if loss_scale == 1.0 else p.grad.detach() * inv) if p.grad is not None else None) for k, p in params.items()}
     for p in params.values():
         p.requires_grad_(False)
     out = dict(comp)

@@ -30,32 +30,37 @@ def _put(state, prefix, mod):
         state[f"{prefix}.{k}"] = v.detach().clone()
 
 
-def _double_conv_state(state, prefix, cin, cout, cmid=None):
+def _double_conv_state(state, prefix, cin, cout, cmid=None, norm="bn", num_domains=None):
     # unet_parts.py:11-22 : conv(no bias) bn relu conv(no bias) bn relu -> indices 0,1,3,4
     cmid = cmid or cout
     _put(state, f"{prefix}.0", nn.Conv2d(cin, cmid, 3, padding=1, bias=False))
-    _put(state, f"{prefix}.1", nn.BatchNorm2d(cmid))
+    _norm_state(state, f"{prefix}.1", cmid, norm, num_domains)
     _put(state, f"{prefix}.3", nn.Conv2d(cmid, cout, 3, padding=1, bias=False))
-    _put(state, f"{prefix}.4", nn.BatchNorm2d(cout))
+    _norm_state(state, f"{prefix}.4", cout, norm, num_domains)
 
 
-def init_unet_a(n_channels, n_classes, bilinear=False, seed=None):
-    """State of ``unet_model.UNet(n_channels, n_classes, bilinear)`` (unet_model.py:7-23)."""
+def init_unet_a(n_channels, n_classes, bilinear=False, seed=None, norm="bn", num_domains=None):
+    """State of ``unet_model.UNet(n_channels, n_classes, bilinear)`` (unet_model.py:7-23).
+    ``norm='dsbn'`` is NOT upstream: UNet-A with every BatchNorm2d replaced by the reference's
+    ``DomainSpecificBatchNorm2d`` (dsbn.py:4-34; keys ``....1.bns.{d}.*``) -- the tensor-bound model of
+    BASELINE.json configs[2] ("DSBN over 3 domains").  BatchNorm construction draws no random numbers, so
+    the conv weights equal those of the plain model for the same seed."""
     if seed is not None:
         torch.manual_seed(seed)
     st = OrderedDict()
-    _double_conv_state(st, "inc.double_conv", n_channels, 64)
+    kw = dict(norm=norm, num_domains=num_domains)
+    _double_conv_state(st, "inc.double_conv", n_channels, 64, **kw)
     factor = 2 if bilinear else 1
     widths = [(64, 128), (128, 256), (256, 512), (512, 1024 // factor)]
     for i, (a, b) in enumerate(widths, 1):
-        _double_conv_state(st, f"down{i}.maxpool_conv.1.double_conv", a, b)
+        _double_conv_state(st, f"down{i}.maxpool_conv.1.double_conv", a, b, **kw)
     ups = [(1024, 512 // factor), (512, 256 // factor), (256, 128 // factor), (128, 64)]
     for i, (a, b) in enumerate(ups, 1):
         if bilinear:
-            _double_conv_state(st, f"up{i}.conv.double_conv", a, b, a // 2)
+            _double_conv_state(st, f"up{i}.conv.double_conv", a, b, a // 2, **kw)
         else:
             _put(st, f"up{i}.up", nn.ConvTranspose2d(a, a // 2, kernel_size=2, stride=2))
-            _double_conv_state(st, f"up{i}.conv.double_conv", a, b)
+            _double_conv_state(st, f"up{i}.conv.double_conv", a, b, **kw)
     _put(st, "outc.conv", nn.Conv2d(64, n_classes, kernel_size=1))
     return st
 
@@ -81,39 +86,42 @@ def _kaiming_fan_out(state, activation="relu"):
             v.fill_(0.0)
 
 
-def _convd_state(st, p, cin, c, norm):
+def _convd_state(st, p, cin, c, norm, num_domains=None):
     for j, ci in ((1, cin), (2, c), (3, c)):
         _put(st, f"{p}.conv{j}", nn.Conv2d(ci, c, 3, 1, 1, bias=True))
-        _norm_state(st, f"{p}.bn{j}", c, norm)
+        _norm_state(st, f"{p}.bn{j}", c, norm, num_domains)
 
 
-def _convu_state(st, p, planes, norm, first):
+def _convu_state(st, p, planes, norm, first, num_domains=None):
     if not first:
         _put(st, f"{p}.conv1", nn.Conv2d(2 * planes, planes, 3, 1, 1, bias=True))
-        _norm_state(st, f"{p}.bn1", planes, norm)
+        _norm_state(st, f"{p}.bn1", planes, norm, num_domains)
     _put(st, f"{p}.conv2", nn.Conv2d(planes, planes // 2, 1, 1, 0, bias=True))
-    _norm_state(st, f"{p}.bn2", planes // 2, norm)
+    _norm_state(st, f"{p}.bn2", planes // 2, norm, num_domains)
     _put(st, f"{p}.conv3", nn.Conv2d(planes, planes, 3, 1, 1, bias=True))
-    _norm_state(st, f"{p}.bn3", planes, norm)
+    _norm_state(st, f"{p}.bn3", planes, norm, num_domains)
 
 
 def init_unet_b(n_channels=3, n_classes=2, n=16, norm="bn", seed=None, head="out1",
-                encoder=True, decoder=True):
-    """State of ``networks.unet.UNet`` (unet.py:299-319); ``Encoder``/``Decoder`` via flags."""
+                encoder=True, decoder=True, num_domains=None):
+    """State of ``networks.unet.UNet`` (unet.py:299-319); ``Encoder``/``Decoder`` via flags.
+    ``norm='dsbn', num_domains=k``: the patched network of SURVEY A2(ii) (upstream raises TypeError at
+    construction because ConvD/ConvU do not pass ``num_domains`` on, unet.py:38,82)."""
     if seed is not None:
         torch.manual_seed(seed)
     st = OrderedDict()
+    nd = num_domains
     if encoder:
-        _convd_state(st, "convd1", n_channels, n, norm)
-        _convd_state(st, "convd2", n, 2 * n, norm)
-        _convd_state(st, "convd3", 2 * n, 4 * n, norm)
-        _convd_state(st, "convd4", 4 * n, 8 * n, norm)
-        _convd_state(st, "convd5", 8 * n, 16 * n, norm)
+        _convd_state(st, "convd1", n_channels, n, norm, nd)
+        _convd_state(st, "convd2", n, 2 * n, norm, nd)
+        _convd_state(st, "convd3", 2 * n, 4 * n, norm, nd)
+        _convd_state(st, "convd4", 4 * n, 8 * n, norm, nd)
+        _convd_state(st, "convd5", 8 * n, 16 * n, norm, nd)
     if decoder:
-        _convu_state(st, "convu4", 16 * n, norm, True)
-        _convu_state(st, "convu3", 8 * n, norm, False)
-        _convu_state(st, "convu2", 4 * n, norm, False)
-        _convu_state(st, "convu1", 2 * n, norm, False)
+        _convu_state(st, "convu4", 16 * n, norm, True, nd)
+        _convu_state(st, "convu3", 8 * n, norm, False, nd)
+        _convu_state(st, "convu2", 4 * n, norm, False, nd)
+        _convu_state(st, "convu1", 2 * n, norm, False, nd)
         _put(st, head, nn.Conv2d(2 * n, n_classes, 3, padding=1))
     _kaiming_fan_out(st)
     return st
@@ -167,19 +175,20 @@ def _dsbn(st, p, x, domain_label, training):
     return _bn(st, f"{p}.bns.{int(domain_label[0])}", x, training)
 
 
-def _double_conv(st, p, x, training):
-    x = F.relu(_bn(st, p + ".1", F.conv2d(x, st[p + ".0.weight"], None, 1, 1), training))
-    x = F.relu(_bn(st, p + ".4", F.conv2d(x, st[p + ".3.weight"], None, 1, 1), training))
+def _double_conv(st, p, x, training, domain_label=None):
+    x = F.relu(_norm(st, p + ".1", F.conv2d(x, st[p + ".0.weight"], None, 1, 1), training, domain_label))
+    x = F.relu(_norm(st, p + ".4", F.conv2d(x, st[p + ".3.weight"], None, 1, 1), training, domain_label))
     return x
 
 
-def unet_a_forward(st, x, training=True, feature=False, bilinear=False):
-    """``unet_model.UNet.forward`` (unet_model.py:25-39)."""
-    x1 = _double_conv(st, "inc.double_conv", x, training)
+def unet_a_forward(st, x, training=True, feature=False, bilinear=False, domain_label=None):
+    """``unet_model.UNet.forward`` (unet_model.py:25-39).  ``domain_label`` only for the DSBN extension
+    (``init_unet_a(norm='dsbn')``); None = upstream."""
+    x1 = _double_conv(st, "inc.double_conv", x, training, domain_label)
     skips = [x1]
     h = x1
     for i in range(1, 5):
-        h = _double_conv(st, f"down{i}.maxpool_conv.1.double_conv", F.max_pool2d(h, 2), training)
+        h = _double_conv(st, f"down{i}.maxpool_conv.1.double_conv", F.max_pool2d(h, 2), training, domain_label)
         skips.append(h)
     for i in range(1, 5):
         skip = skips[4 - i]
@@ -189,7 +198,7 @@ def unet_a_forward(st, x, training=True, feature=False, bilinear=False):
             h = F.conv_transpose2d(h, st[f"up{i}.up.weight"], st[f"up{i}.up.bias"], stride=2)
         dy, dx = skip.size(2) - h.size(2), skip.size(3) - h.size(3)
         h = F.pad(h, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])      # unet_parts.py:62-63
-        h = _double_conv(st, f"up{i}.conv.double_conv", torch.cat([skip, h], 1), training)
+        h = _double_conv(st, f"up{i}.conv.double_conv", torch.cat([skip, h], 1), training, domain_label)
     logits = F.conv2d(h, st["outc.conv.weight"], st["outc.conv.bias"])
     return (logits, h) if feature else logits
 

@@ -67,7 +67,7 @@ def test_product_does_not_import_oracle():
             text = open(os.path.join(ROOT, "tools", f)).read()
             assert "from oracle" not in text and "import oracle" not in text, f"tools/{f} imports the oracle"
     bench = open(os.path.join(ROOT, "bench.py")).read()
-    gpu_arm = bench[bench.index("def run_ours("):bench.index("def cpu_step_time(")]
+    gpu_arm = bench[bench.index("def run_ours("):bench.index("def oracle_models(")]      # the baseline legs (cpu / eager-gpu / reference arm) follow
     assert gpu_arm and "oracle" not in gpu_arm.replace("no oracle on this arm", ""), "bench.py GPU arm touches the oracle"
 
 
@@ -89,6 +89,11 @@ def test_state_dict_layout_matches_oracle_init():
     assert list(sd) == list(st) and len(sd) == 184
     assert all(torch.equal(sd[k], st[k]) for k in sd)
     assert len(list(b.parameters())) == 106
+    for mk, init in ((lambda: B.UNet(3, 2, norm="dsbn", num_domains=3), lambda: U.init_unet_b(3, 2, seed=1337, norm="dsbn", num_domains=3)),
+                     (lambda: UNet(3, 2, norm="dsbn", num_domains=3), lambda: U.init_unet_a(3, 2, seed=1337, norm="dsbn", num_domains=3))):
+        torch.manual_seed(1337)
+        sd, st = mk().state_dict(), init()
+        assert list(sd) == list(st) and all(torch.equal(sd[k], st[k]) for k in sd)
     torch.manual_seed(1337)
     r = B.Rec_Decoder(num_classes=2, norm="dsbn", num_domains=3)
     st = U.init_rec_decoder(num_classes=2, norm="dsbn", num_domains=3, seed=1337)

@@ -74,6 +74,72 @@ def test_dsbn_golden():
         U._dsbn({}, "x", torch.zeros(2, 3), [0], True)
 
 
+def test_unet_b_dsbn_golden():
+    """UNet-B with DSBN threaded through ConvD/ConvU.  The fixture is the output of the REFERENCE's own
+    modules under the documented run-time patch of oracle/make_golden.py::_DsbnPatch (``normalization`` passes
+    ``num_domains`` on, ``DSBN.forward`` takes its label from a context variable): 6 lines, none of them arithmetic."""
+    dl = torch.tensor([1, 2])
+    _model_case("unet_b_dsbn3_c3_k2_32.npz", lambda: U.init_unet_b(3, 2, seed=1337, norm="dsbn", num_domains=3),
+                lambda s, x: U.unet_b_forward(s, x, True, domain_label=dl), 2)
+    with pytest.raises(TypeError):      # the label is mandatory for a DSBN network
+        U.unet_b_forward(U.init_unet_b(3, 2, seed=0, norm="dsbn", num_domains=2), torch.zeros(1, 3, 16, 16), True)
+
+
+def step_domains(d_lb, d_ulb, B):
+    """Same convention as oracle/make_golden.py::step_domains."""
+    u, l = torch.full((B,), d_ulb, dtype=torch.long), torch.full((B,), d_lb, dtype=torch.long)
+    return dict(t1=u, t2=u, t3=l, s0=u, lb=l, ul=u, lu=l, s=u, lq=u)
+
+
+def test_dsbn_step_golden():
+    path = os.path.join(GOLDEN, "dsbnstep_b_softmax_c3_k2_32_b2_it3000_d02of3.npz")
+    fx = np.load(path)
+    torch.manual_seed(1337)
+    st_s, st_t = U.init_unet_b(3, 2, norm="dsbn", num_domains=3), U.init_unet_b(3, 2, norm="dsbn", num_domains=3)
+    batch = S.synthetic_batch(3, 2, 32, 32, 2, 2, seed=1337)
+    out = S.ssl_step(lambda s, x, dl: U.unet_b_forward(s, x, True, domain_label=dl), st_s, st_t, {}, batch, n_classes=2, iter_num=3000,
+                     max_iterations=30000, lr=0.03, threshold=float(fx["threshold"]), domains=step_domains(int(fx["d_lb"]), int(fx["d_ulb"]), 2))
+    assert float(out["loss"]) == float(fx["loss"])
+    assert sorted(k for k, v in out["grads"].items() if v is None) == sorted(fx["no_grad_params"].tolist())
+    assert all(".bns.1." in k for k in fx["no_grad_params"].tolist())          # domain 1 is not in play: no gradient, no SGD, no weight decay
+    for k_, v in st_s.items():
+        np.testing.assert_allclose(_digest(v), fx["student_after/" + k_], rtol=1e-12, atol=0, err_msg=k_)
+    for k_, v in st_t.items():
+        np.testing.assert_allclose(_digest(v), fx["teacher_after/" + k_], rtol=1e-12, atol=0, err_msg=k_)
+    # running statistics: only the domains in play were updated
+    for k_, v in st_s.items():
+        if k_.endswith("num_batches_tracked") and ".bns." in k_:
+            d = int(k_.split(".bns.")[1].split(".")[0])
+            assert int(v) == {0: 2, 1: 0, 2: 3}[d], (k_, int(v))                 # labelled domain: lb, lu; unlabelled: s0, ul, s
+
+
+def test_unet_a_dsbn_extension_equals_plain_bn_per_domain():
+    """UNet-A has no DSBN upstream; the extension (init_unet_a(norm='dsbn')) must be exactly the plain network run with the
+    selected domain's BatchNorm tensors."""
+    st = U.init_unet_a(1, 2, seed=3, norm="dsbn", num_domains=2)
+    plain = U.init_unet_a(1, 2, seed=3)
+    for k in plain:
+        if k.endswith(".weight") and plain[k].dim() == 4:
+            assert torch.equal(plain[k], st[k])
+    x = torch.rand(2, 1, 32, 32)
+    sel = {k.replace(".bns.1", ""): v.clone() for k, v in st.items() if ".bns.0." not in k}
+    assert list(sel.keys()) == list(plain.keys())
+    assert torch.equal(U.unet_a_forward(st, x, True, domain_label=torch.tensor([1, 1])), U.unet_a_forward(sel, x, True))
+    assert int(st["inc.double_conv.1.bns.0.num_batches_tracked"]) == 0 and int(st["inc.double_conv.1.bns.1.num_batches_tracked"]) == 1
+
+
+def test_loss_scale_is_a_noop_in_fp32():
+    torch.manual_seed(1337)
+    a, b = U.init_unet_b(1, 2, seed=5), U.init_unet_b(1, 2, seed=5)
+    batch = S.synthetic_batch(1, 2, 16, 16, 2, 2, seed=3)
+    fwd = lambda s, x: U.unet_b_forward(s, x, True)
+    o1 = S.ssl_step(fwd, a, {k: v.clone() for k, v in a.items()}, {}, batch, n_classes=2, threshold=0.6, iter_num=3000, update=False)
+    o2 = S.ssl_step(fwd, b, {k: v.clone() for k, v in b.items()}, {}, batch, n_classes=2, threshold=0.6, iter_num=3000, update=False, loss_scale=1024.0)
+    for k in o1["grads"]:
+        if o1["grads"][k] is not None:
+            assert torch.allclose(o1["grads"][k], o2["grads"][k], rtol=1e-5, atol=1e-9), k
+
+
 def test_losses_golden():
     fx = np.load(os.path.join(GOLDEN, "losses.npz"))
     for C in (2, 3, 4):

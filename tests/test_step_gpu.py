@@ -21,6 +21,33 @@ def _digest(v):
     return np.concatenate([[v.sum().item(), v.abs().sum().item()], v[:4].numpy()]).astype(np.float64)
 
 
+def check_state_after(fx, student, teacher, before):
+    """State after SGD(momentum, wd) + EMA: weights, BN running statistics (forward order!), num_batches_tracked.
+    Fingerprints per tensor: (sum, abs-sum, first 4 values).  Running statistics and the abs-sum are well conditioned
+    (2e-4).  Individual weight entries move by lr * gradient, and single gradient entries of these random-init BatchNorm
+    networks are ill-conditioned even between two fp32 evaluations (the fp32 CPU reference is only
+    within 3e-3..1e-2 of float64): the UPDATE of the first entries must agree within 15 % of the largest update."""
+    for state, tag, st0 in ((student.state_dict(), "student_after/", before[0]), (teacher.state_dict(), "teacher_after/", before[1])):
+        for k_, v in state.items():
+            ref = fx[tag + k_]
+            got = _digest(v)
+            if k_.endswith("num_batches_tracked"):
+                assert got[0] == ref[0], k_
+                continue
+            scale = max(abs(ref[1]), 1e-12)                       # abs-sum of the tensor
+            if "running_" in k_:
+                assert abs(got[1] - ref[1]) <= 2e-4 * scale, (tag + k_, got[1], ref[1])
+                assert np.all(np.abs(got[2:] - ref[2:]) <= 2e-4 * max(np.abs(ref[2:]).max(), 1e-3)), (tag + k_, got[2:], ref[2:])
+            else:
+                w0f = st0[k_].double().flatten()
+                w0 = w0f[:4].numpy()
+                upd_ref, upd_got = ref[2:2 + len(w0)] - w0, got[2:2 + len(w0)] - w0
+                assert np.all(np.abs(upd_got - upd_ref) <= 0.15 * np.abs(upd_ref).max() + 1e-6), (tag + k_, upd_got, upd_ref)
+                # abs-sum: 2e-4 of the tensor plus 2 % of (an estimate of) the total update
+                upd_total = max(abs(ref[1] - float(w0f.abs().sum())), float(np.abs(upd_ref).mean()) * v.numel())
+                assert abs(got[1] - ref[1]) <= 2e-4 * scale + 0.02 * upd_total, (tag + k_, got[1], ref[1], upd_total)
+
+
 def _run(path, precision):
     from networks import unet as unet_b
     from networks import unet_model as unet_a
@@ -69,30 +96,7 @@ def test_step_fp32_matches_reference_fixture(path):
     for key in PLANES:
         got, want = out[key].cpu().numpy().astype(np.uint8), fx["comp/" + key].astype(np.uint8).reshape(out[key].shape)
         assert (got == want).mean() >= 0.999, (key, float((got == want).mean()))
-    # state after SGD(momentum, wd) + EMA: weights, BN running statistics (forward order!), num_batches_tracked.
-    # Fingerprints per tensor: (sum, abs-sum, first 4 values).  Running statistics and the abs-sum are well conditioned
-    # (2e-4).  Individual weight entries move by lr * gradient, and single gradient entries of these random-init BatchNorm
-    # networks are ill-conditioned even between two fp32 evaluations (the fp32 CPU reference is only
-    # within 3e-3..1e-2 of float64): the UPDATE of the first entries must agree within 15 % of the largest update.
-    for state, tag, st0 in ((student.state_dict(), "student_after/", before[0]), (teacher.state_dict(), "teacher_after/", before[1])):
-        for k_, v in state.items():
-            ref = fx[tag + k_]
-            got = _digest(v)
-            if k_.endswith("num_batches_tracked"):
-                assert got[0] == ref[0], k_
-                continue
-            scale = max(abs(ref[1]), 1e-12)                       # abs-sum of the tensor
-            if "running_" in k_:
-                assert abs(got[1] - ref[1]) <= 2e-4 * scale, (tag + k_, got[1], ref[1])
-                assert np.all(np.abs(got[2:] - ref[2:]) <= 2e-4 * max(np.abs(ref[2:]).max(), 1e-3)), (tag + k_, got[2:], ref[2:])
-            else:
-                w0f = st0[k_].double().flatten()
-                w0 = w0f[:4].numpy()
-                upd_ref, upd_got = ref[2:2 + len(w0)] - w0, got[2:2 + len(w0)] - w0
-                assert np.all(np.abs(upd_got - upd_ref) <= 0.15 * np.abs(upd_ref).max() + 1e-6), (tag + k_, upd_got, upd_ref)
-                # abs-sum: 2e-4 of the tensor plus 2 % of (an estimate of) the total update
-                upd_total = max(abs(ref[1] - float(w0f.abs().sum())), float(np.abs(upd_ref).mean()) * v.numel())
-                assert abs(got[1] - ref[1]) <= 2e-4 * scale + 0.02 * upd_total, (tag + k_, got[1], ref[1], upd_total)
+    check_state_after(fx, student, teacher, before)
     assert tr.iter_num == int(os.path.basename(path)[:-4].split("_")[7][2:]) + 1
 
 

@@ -7,7 +7,12 @@ namespace ustrun {
 
 __global__ void __launch_bounds__(256) k_sgd_ema(const ustrun_param_t* __restrict__ table, const int* __restrict__ blk_tensor,
                                                 const long long* __restrict__ blk_offset, float lr, float mu, float wd, float alpha,
-                                                float gscale, int do_sgd, int do_ema) {
+                                                float gscale, int do_sgd, int do_ema, const float* __restrict__ hyper) {
+  if (hyper) {            // per-step scalars in device memory: a captured CUDA graph replays with new values
+    lr = hyper[0];
+    alpha = hyper[1];
+    gscale = hyper[2];
+  }
   const ustrun_param_t t = table[blk_tensor[blockIdx.x]];
   const long long off = blk_offset[blockIdx.x];
   long long cnt = t.n - off;
@@ -63,6 +68,13 @@ using namespace ustrun;
 extern "C" int ustrun_sgd_ema_multi(const ustrun_param_t* table, const int* blk_tensor, const long long* blk_offset, int nblocks, float lr,
                                     float momentum, float weight_decay, float alpha, float grad_scale, int do_sgd, int do_ema, void* stream) {
   USTRUN_REQUIRE(table && blk_tensor && blk_offset && nblocks > 0, "sgd_ema_multi: bad args");
-  k_sgd_ema<<<nblocks, 256, 0, (cudaStream_t)stream>>>(table, blk_tensor, blk_offset, lr, momentum, weight_decay, alpha, grad_scale, do_sgd, do_ema);
+  k_sgd_ema<<<nblocks, 256, 0, (cudaStream_t)stream>>>(table, blk_tensor, blk_offset, lr, momentum, weight_decay, alpha, grad_scale, do_sgd, do_ema, nullptr);
   return check_launch("sgd_ema_multi");
+}
+
+extern "C" int ustrun_sgd_ema_multi_dev(const ustrun_param_t* table, const int* blk_tensor, const long long* blk_offset, int nblocks,
+                                        const float* hyper, float momentum, float weight_decay, int do_sgd, int do_ema, void* stream) {
+  USTRUN_REQUIRE(table && blk_tensor && blk_offset && nblocks > 0 && hyper, "sgd_ema_multi_dev: bad args");
+  k_sgd_ema<<<nblocks, 256, 0, (cudaStream_t)stream>>>(table, blk_tensor, blk_offset, 0.f, momentum, weight_decay, 0.f, 1.f, do_sgd, do_ema, hyper);
+  return check_launch("sgd_ema_multi_dev");
 }

@@ -69,6 +69,7 @@ _SIGS = {
     "ustrun_bn_finalize_peer": [p, i32, i32, f64, p, p, p, p, p, p, f32, f32, p, p, p, p, p, i32, i32, C.c_uint, p, p, p],
     "ustrun_bn_bwd_finalize_peer": [p, i32, i32, f64, p, p, p, p, i32, p, p, i32, i32, C.c_uint, p, p, p],
     "ustrun_sgd_ema_multi": [p, p, p, i32, f32, f32, f32, f32, f32, i32, i32, p],
+    "ustrun_sgd_ema_multi_dev": [p, p, p, i32, p, f32, f32, i32, i32, p],
     "ustrun_fft_amp_mix": [p, p, p, f64, p, i32, i32, i32, i32, p, i64, p],
     "ustrun_hardness": [p, p, i32, i32, i32, i32, i32, p, p, p, p, p],
     "ustrun_encode_labels": [p, i32, i32, i32, i32, p, p],

@@ -112,6 +112,8 @@ class PeerStats:
         self.error = torch.zeros(1, dtype=torch.int32, device=dev)
         self.seq = 0
         self._ctypes = ctypes
+        self._poll_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._poll_ev = None
         torch.cuda.synchronize()
         dist.barrier(grp)
 
@@ -125,6 +127,21 @@ class PeerStats:
     def check(self):
         if int(self.error.item()) != 0:
             raise RuntimeError("peer BatchNorm reduction timed out waiting for another rank")
+
+    def poll(self):
+        """Non-blocking check of the device-side timeout flag: raises if a finalize kernel of an EARLIER step gave up waiting
+        for a peer (it then continued with this rank's local sums, i.e. unsynchronised statistics).  An asynchronous copy of
+        the flag is enqueued on every call and read on the next one, so a timeout surfaces at most two steps late without
+        ever synchronising the stream."""
+        if self._poll_ev is not None and self._poll_ev.query():
+            if int(self._poll_host[0]) != 0:
+                raise RuntimeError("peer BatchNorm reduction timed out waiting for another rank: BatchNorm statistics of that step "
+                                   "were not synchronised (a rank stalled for longer than the kernel's timeout)")
+            self._poll_ev = None
+        if self._poll_ev is None:
+            self._poll_host.copy_(self.error, non_blocking=True)
+            self._poll_ev = torch.cuda.Event()
+            self._poll_ev.record()
 
 
 class _BNSync:
@@ -155,6 +172,7 @@ class DataParallel:
         # otherwise each rank has its own loss and gradients are averaged (plain DDP semantics).
         self.global_loss = global_loss
         self.peer = None
+        self.graph_safe = False          # per-layer sequence numbers of the peer-BN kernels are launch arguments: no graph replay
         if sync_bn and self.world > 1:
             # sync_bn="peer" (default on GPUs): finalize kernels reduce over NVLink peer memory themselves;
             # sync_bn="nccl": one NCCL all-reduce per layer and pass (validation / CPU tests)

@@ -93,13 +93,17 @@ def set_wgrad_overlap(flag: bool) -> None:
 
 
 def _side_stream():
-    if not _WGRAD_OVERLAP or PROFILE_EVENTS is not None or torch.cuda.is_current_stream_capturing():
+    if not _WGRAD_OVERLAP or PROFILE_EVENTS is not None:
         return None
     dev = torch.cuda.current_device()
     st = _SIDE.get(dev)
     if st is None:
         st = _SIDE[dev] = torch.cuda.Stream(device=dev)
     return st
+
+
+_HELD: List = []          # operands of side-stream kernels enqueued during a CUDA-graph capture (see on_side_stream)
+_SIDE_DIRTY = [False]     # the side stream has work the current stream has not joined yet
 
 
 def on_side_stream(fn: Callable, tensors) -> None:
@@ -114,17 +118,25 @@ def on_side_stream(fn: Callable, tensors) -> None:
     ev = torch.cuda.Event()
     ev.record()
     with torch.cuda.stream(side):
-        side.wait_event(ev)
+        side.wait_event(ev)               # during a capture this forks the side stream into the graph
         fn()
-    for t in tensors:
-        t.record_stream(side)           # the caching allocator must not recycle them under the side stream
+    _SIDE_DIRTY[0] = True
+    if torch.cuda.is_current_stream_capturing():
+        # record_stream would keep the blocks out of the capture's private pool until the capture ends (its events cannot be
+        # queried inside a capture): hold references until the join instead -- allocations after the join are ordered after it
+        _HELD.extend(tensors)
+    else:
+        for t in tensors:
+            t.record_stream(side)           # the caching allocator must not recycle them under the side stream
 
 
 def join_side_stream() -> None:
     """Make the current stream wait for all weight-gradient kernels (before the optimiser / all-reduce)."""
     st = _SIDE.get(torch.cuda.current_device()) if torch.cuda.is_available() else None
-    if st is not None:
+    if st is not None and _SIDE_DIRTY[0]:
         torch.cuda.current_stream().wait_stream(st)
+        _SIDE_DIRTY[0] = False
+    _HELD.clear()
 
 
 def reserve_pool(nbytes: Optional[int] = None, fraction: float = 0.5, cap: int = 96 << 30) -> int:

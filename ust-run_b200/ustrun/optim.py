@@ -45,6 +45,33 @@ class FusedSGDEMA:
         self._table_dev = torch.empty(len(self.params) * 48, dtype=torch.uint8, device=dev)
         self._table_key = None
 
+    # -- checkpointing: same layout as torch.optim.SGD.state_dict() (utils/util.py:259-273 saves it, train.py:544 restores it)
+    def state_dict(self):
+        state = {}
+        for i, p in enumerate(self.params):
+            if not self.first[i]:
+                state[i] = {"momentum_buffer": self.flat_buf[self.offsets[i]: self.offsets[i] + p.numel()].view(p.shape).clone()}
+        group = {"lr": None, "momentum": self.momentum, "dampening": 0, "weight_decay": self.weight_decay, "nesterov": False,
+                 "maximize": False, "foreach": None, "differentiable": False, "fused": None, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(self.params):
+            raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+        self.momentum = float(groups[0].get("momentum", self.momentum))
+        self.weight_decay = float(groups[0].get("weight_decay", self.weight_decay))
+        self.first = [True] * len(self.params)
+        self.flat_buf.zero_()
+        for pos, key in enumerate(order):
+            st = sd["state"].get(key, sd["state"].get(str(key)))
+            if st is not None and st.get("momentum_buffer") is not None:
+                p = self.params[pos]
+                self.flat_buf[self.offsets[pos]: self.offsets[pos] + p.numel()].view(p.shape).copy_(st["momentum_buffer"])
+                self.first[pos] = False
+        self._table_key = None
+
     def grad_view(self, i):
         p = self.params[i]
         return self.flat_grad[self.offsets[i]: self.offsets[i] + p.numel()].view(p.shape)
@@ -75,12 +102,19 @@ class FusedSGDEMA:
             self._table_key = key
         return self._table_dev
 
-    def step(self, lr, alpha=None, grad_scale=1.0, do_sgd=True):
-        """SGD step with the gradients currently in the flat buffer, then (alpha given) EMA."""
+    def step(self, lr=None, alpha=None, grad_scale=1.0, do_sgd=True, hyper=None, do_ema=None):
+        """SGD step with the gradients currently in the flat buffer, then (alpha given) EMA.
+        ``hyper``: device tensor float32[>=3] = {lr, alpha, grad_scale}; the kernel then reads the per-step scalars from
+        device memory (CUDA-graph replay) and ``lr`` / ``alpha`` / ``grad_scale`` are ignored (``do_ema`` selects the EMA half)."""
         table = self._table()
-        _profiled("hbm_sgd_ema", 28.0 * sum(p.numel() for p in self.params), "ustrun_sgd_ema_multi", _ptr(table), _ptr(self.blk_tensor), _ptr(self.blk_offset), self.nblocks, float(lr), self.momentum,
-              self.weight_decay, float(alpha if alpha is not None else 0.0), float(grad_scale), 1 if do_sgd else 0,
-              1 if alpha is not None else 0, _stream())
+        nbytes = 28.0 * sum(p.numel() for p in self.params)
+        if hyper is not None:
+            _profiled("hbm_sgd_ema", nbytes, "ustrun_sgd_ema_multi_dev", _ptr(table), _ptr(self.blk_tensor), _ptr(self.blk_offset), self.nblocks, _ptr(hyper),
+                      self.momentum, self.weight_decay, 1 if do_sgd else 0, 1 if (do_ema if do_ema is not None else True) else 0, _stream())
+        else:
+            _profiled("hbm_sgd_ema", nbytes, "ustrun_sgd_ema_multi", _ptr(table), _ptr(self.blk_tensor), _ptr(self.blk_offset), self.nblocks, float(lr), self.momentum,
+                      self.weight_decay, float(alpha if alpha is not None else 0.0), float(grad_scale), 1 if do_sgd else 0,
+                      1 if alpha is not None else 0, _stream())
         if do_sgd:
             for i in range(len(self.params)):
                 if self.has_grad[i]:

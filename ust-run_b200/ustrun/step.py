@@ -86,10 +86,26 @@ def mix_input(a, b, box_u8, b_index=None) -> E.Act:
     return out
 
 
+STEP_DOMAIN_TAGS = ("t1", "t2", "t3", "s0", "lb", "ul", "lu", "s", "lq")
+# hyper block layout (float32, device): the per-step scalars every kernel of the step reads from memory
+H_LR, H_ALPHA, H_GSCALE, H_CW, H_CW2, H_ONE = 0, 1, 2, 3, 4, 5
+_HYPER_N = 8
+_HYPER_RING = 4
+
+
+def step_domains(domain_lb, domain_ulb):
+    """Domain label of each forward of a DSBN step.  Upstream has no DSBN step; the convention here: a forward
+    belongs to the domain of the image that fills the area OUTSIDE the CutMix box -- t1 / t2 / s0 / ul / s / lq: the
+    unlabelled batch's domain, t3 / lb / lu: the labelled batch's.  DSBN semantics are the reference's (dsbn.py:24-27):
+    the whole forward batch goes through ``bns[domain_label[0]]``."""
+    u, l = [int(domain_ulb)], [int(domain_lb)]
+    return dict(t1=u, t2=u, t3=l, s0=u, lb=l, ul=u, lu=l, s=u, lq=u)
+
+
 class SSLTrainer:
     def __init__(self, model, ema_model, n_classes, branch="softmax", base_lr=0.03, max_iterations=30000, threshold=0.95,
                  consistency=1.0, consistency_rampup=200.0, ema_decay=0.99, momentum=0.9, weight_decay=1e-4, dp=None,
-                 forward_kwargs=None, fft_window=0.01, hardness_mode=None):
+                 forward_kwargs=None, fft_window=0.01, hardness_mode=None, use_graph=False):
         self.model, self.ema_model = model, ema_model
         self.n_classes, self.branch = n_classes, branch
         self.base_lr, self.lr, self.max_iterations = base_lr, base_lr, max_iterations
@@ -105,15 +121,31 @@ class SSLTrainer:
         self.opt = FusedSGDEMA(self.params, list(ema_model.parameters()), momentum=momentum, weight_decay=weight_decay)
         self._touched = set()
         self._last_branch = False
+        dev = self.params[0].device
+        # per-step scalars live in device memory (lr, EMA alpha, gradient scale, consistency weights): the launch arguments of
+        # a step never change, which is what lets the whole step be captured once as a CUDA graph and replayed
+        self.hyper = torch.zeros(_HYPER_N, dtype=torch.float32, device=dev)
+        self._hyper_host = [torch.zeros(_HYPER_N, dtype=torch.float32).pin_memory() for _ in range(_HYPER_RING)]
+        self._hyper_ev = [None] * _HYPER_RING
+        self._hyper_slot = 0
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
+        self._eager_steps = 0
+        self._eager_by_key = {}
+        self.launches_per_step = 0            # kernels of the last eager / captured step (bench.py: gpu_launches)
+        self._domains = None
 
     # -- helpers ---------------------------------------------------------------------------
     def consistency_weight(self, iter_num):
         return self.consistency * sigmoid_rampup(iter_num // (self.max_iterations / self.consistency_rampup), self.consistency_rampup)
 
-    def _forward(self, model, a: E.Act, need_grad: bool):
+    def _forward(self, model, a: E.Act, need_grad: bool, tag: str = None):
         ctx = E.Ctx(model.training, need_grad, bn_sync=bridge.BN_SYNC)
         ctx.bn_world = bridge.BN_WORLD
-        (logits, head_bwd), = model.program(ctx, a, **self.forward_kwargs)
+        kw = self.forward_kwargs
+        if self._domains is not None:
+            kw = dict(kw, domain_label=self._domains[tag])
+        (logits, head_bwd), = model.program(ctx, a, **kw)
         return ctx, logits, head_bwd
 
     def _grad_provider(self, param):
@@ -122,20 +154,46 @@ class SSLTrainer:
             self.dp.on_grad_requested(param, self._last_branch)
         return self.opt.grad_for(param)
 
-    def _branch(self, a, target_u8, mask_u8, weight):
-        """forward -> loss -> backward of one loss branch; returns loss3 device tensor."""
-        ctx, logits, head_bwd = self._forward(self.model, a, True)
+    def _branch(self, a, target_u8, mask_u8, weight_idx, tag):
+        """forward -> loss -> backward of one loss branch; returns loss3 device tensor.  ``weight_idx``: slot of the hyper
+        block holding this term's outer weight (1, cw, cw, cw^2: train.py:838)."""
+        ctx, logits, head_bwd = self._forward(self.model, a, True, tag)
         if self.dp is not None and self.dp.global_loss:
             loss3, coef = term_forward(logits, target_u8, mask_u8, self.branch, allreduce=self.dp.sum_across_ranks, world=self.dp.world)
         else:
             loss3, coef = term_forward(logits, target_u8, mask_u8, self.branch)
-        dlogits = term_backward(logits, target_u8, mask_u8, self.branch, coef, gscale=weight)
+        dlogits = term_backward(logits, target_u8, mask_u8, self.branch, coef, upstream=self.hyper[weight_idx:weight_idx + 1])
         sink = E.GradSink(provider=self._grad_provider)
         head_bwd(dlogits, sink)
         ctx.backward(sink)
         if self.dp is not None:
             self.dp.on_branch_done()
         return loss3, logits
+
+    def _set_hyper(self, it, gscale):
+        """Write this step's scalars (host double arithmetic exactly as train.py:819-820,838,91,854) to the device block."""
+        cw = self.consistency_weight(it)
+        alpha = min(1 - 1 / (it + 1), self.ema_decay)
+        slot = self._hyper_slot
+        self._hyper_slot = (slot + 1) % _HYPER_RING
+        if self._hyper_ev[slot] is not None:
+            self._hyper_ev[slot].synchronize()          # the copy that last used this pinned slot (4 steps ago) has completed
+        h = self._hyper_host[slot]
+        h[H_LR], h[H_ALPHA], h[H_GSCALE], h[H_CW], h[H_CW2], h[H_ONE] = self.lr, alpha, gscale, cw, cw * cw, 1.0
+        self.hyper.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_ev[slot] = ev
+        return cw
+
+    # -- checkpointing (utils/util.py:259-297 saves the optimizer state; train.py:542-548 restores it and iter_num) ----------
+    def state_dict(self):
+        return {"optimizer": self.opt.state_dict(), "iter_num": self.iter_num, "lr": self.lr}
+
+    def load_state_dict(self, sd):
+        self.opt.load_state_dict(sd["optimizer"])
+        self.iter_num, self.lr = int(sd["iter_num"]), float(sd["lr"])
+        self._graphs = {}
 
     # -- the step ----------------------------------------------------------------------------
     def step(self, batch, lq=None, keep_logits=False):
@@ -144,9 +202,73 @@ class SSLTrainer:
         box [Bu,H,W] {0,1}, choice [Bu] int, cut_img [Nc,C,H,W],
         cut_label, cut_mask (labelled batch + confidence bank).  ``lq``: optional [1,C,H,W] image
         whose student forward only updates BN running statistics (train.py:740).
-        Returns device tensors (losses, compositions); nothing is copied to the host."""
-        b = batch
+        DSBN networks: ``domain_lb`` / ``domain_ulb`` (host ints; see ``step_domains``).
+        Returns device tensors (losses, compositions); nothing is copied to the host.  With ``use_graph`` the returned
+        tensors are the graph's static outputs: read them before the next ``step``."""
         it = self.iter_num
+        if self.dp is not None and getattr(self.dp, "peer", None) is not None:
+            self.dp.peer.poll()                     # a peer-BN timeout of an earlier step raises here (one step late, no sync)
+        gscale = 1.0 if self.dp is None else (1.0 if self.dp.global_loss else 1.0 / self.dp.world)
+        domains = None
+        if "domain_lb" in batch or "domain_ulb" in batch:
+            domains = step_domains(int(batch["domain_lb"]), int(batch["domain_ulb"]))
+        tensors = {k: v for k, v in batch.items() if isinstance(v, torch.Tensor)}
+        key = None
+        if self.use_graph:
+            dom_key = None if domains is None else tuple(domains[t][0] for t in STEP_DOMAIN_TAGS)
+            key = (tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in tensors.items())), None if lq is None else tuple(lq.shape), bool(keep_logits),
+                   dom_key, bool(self.first_epoch), self.hardness_mode, E.get_precision())
+        # the first two steps of every input signature run eagerly: they size the allocator pool, initialise the momentum
+        # buffers (the optimiser's descriptor table changes after step 0) and set the per-kernel launch attributes
+        if key is not None and self._eager_by_key.get(key, 0) >= 2:
+            out, cw = self._step_graphed(key, tensors, lq, keep_logits, domains, it, gscale)
+        else:
+            cw = self._set_hyper(it, gscale)
+            k0 = E.KERNELS
+            out = self._step_body(tensors, lq, keep_logits, domains)
+            self.launches_per_step = E.KERNELS - k0
+            self._eager_steps += 1
+            if key is not None:
+                self._eager_by_key[key] = self._eager_by_key.get(key, 0) + 1
+        # the reference's lr schedule (train.py:854-858)
+        self.lr = self.base_lr * (1.0 - it / self.max_iterations) ** 0.9
+        self.iter_num = it + 1
+        out = dict(out)
+        out["consistency_weight"] = cw
+        return out
+
+    def _step_graphed(self, key, tensors, lq, keep_logits, domains, it, gscale):
+        """Replay the step as ONE CUDA graph (captured on first use per input signature): ~1300 (UNet-A) / ~2000 (UNet-B)
+        kernel launches leave the host as a single cudaGraphLaunch; inputs are copied into the capture's static buffers."""
+        if self.dp is not None and not self.dp.graph_safe:
+            raise NotImplementedError("CUDA-graph replay of this data-parallel configuration is not enabled")
+        ent = self._graphs.get(key)
+        if ent is None:
+            static = {k: v.detach().to(self.hyper.device, copy=True) for k, v in tensors.items()}
+            static_lq = None if lq is None else lq.detach().to(self.hyper.device, copy=True)
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()                 # the eager warm-up's cached blocks go back to the driver: the capture gets its own pool
+            g = torch.cuda.CUDAGraph()
+            k0 = E.KERNELS
+            with torch.cuda.graph(g):
+                out = self._step_body(static, static_lq, keep_logits, domains)
+            ent = self._graphs[key] = (g, static, static_lq, out, E.KERNELS - k0, list(self.opt.has_grad))
+        g, static, static_lq, out, self.launches_per_step, has_grad = ent
+        if has_grad != self.opt.has_grad:            # another signature (DSBN domains) ran in between: restore this graph's descriptor table
+            for i, f in enumerate(has_grad):
+                self.opt.set_has_grad(i, f)
+        self.opt._table()
+        for k, v in tensors.items():
+            static[k].copy_(v, non_blocking=True)
+        if lq is not None:
+            static_lq.copy_(lq, non_blocking=True)
+        cw = self._set_hyper(it, gscale)
+        g.replay()
+        return out, cw
+
+    def _step_body(self, b, lq, keep_logits, domains):
+        """Device work of one step on the current stream; every per-step scalar comes from ``self.hyper``."""
+        self._domains = domains
         branch = self.branch
         dev = b["ulb_w"].device
         box_u8 = as_u8(b["box"]).contiguous()
@@ -159,46 +281,43 @@ class SSLTrainer:
             b = dict(b)
             b["move_transx"] = amp_mix(b["cut_img"].float()[choice_i.long()], b["ulb_w"], b["mix_ratio"], self.fft_window)
         # 1. teacher
-        _, t1, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], None, None), False)
-        _, t2, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], b["cut_img"], box_u8, choice_i), False)
-        _, t3, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], b["cut_img"], inv_box, choice_i), False)
+        _, t1, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], None, None), False, "t1")
+        _, t2, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], b["cut_img"], box_u8, choice_i), False, "t2")
+        _, t3, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], b["cut_img"], inv_box, choice_i), False, "t3")
         # 2. student on ulb_w (no grad)
-        _, s0, _ = self._forward(self.model, mix_input(b["ulb_w"], None, None), False)
+        _, s0, _ = self._forward(self.model, mix_input(b["ulb_w"], None, None), False, "s0")
         # 3. pseudo labels
         comp = pseudo_labels(t1, t2, t3, box_u8, b["cut_label"], b["cut_mask"], choice_i, self.threshold, branch, student_logits=s0)
         # 4. four loss branches
-        cw = self.consistency_weight(it)
         self.opt.zero_grad()
         self._touched = set()
         if self.dp is not None:
             self.dp.begin_step(self.opt)
         lb_t = as_u8(b["lb_mask"]).contiguous()
-        l_sup, lg_lb = self._branch(mix_input(b["lb_x"], None, None), lb_t, None, 1.0)
-        l_ul, lg_ul = self._branch(mix_input(b["ulb_s"], b["move_transx"], box_u8), comp["pseudo_label_ul"], comp["mask_ul"], cw)
-        l_lu, lg_lu = self._branch(mix_input(b["move_transx"], b["ulb_s"], box_u8), comp["pseudo_label_lu"], comp["mask_lu"], cw)
+        l_sup, lg_lb = self._branch(mix_input(b["lb_x"], None, None), lb_t, None, H_ONE, "lb")
+        l_ul, lg_ul = self._branch(mix_input(b["ulb_s"], b["move_transx"], box_u8), comp["pseudo_label_ul"], comp["mask_ul"], H_CW, "ul")
+        l_lu, lg_lu = self._branch(mix_input(b["move_transx"], b["ulb_s"], box_u8), comp["pseudo_label_lu"], comp["mask_lu"], H_CW, "lu")
         self._last_branch = True          # from here on finished gradient buckets may be all-reduced
-        l_s, lg_s = self._branch(mix_input(b["ulb_s"], None, None), comp["pseudo_label_w"], comp["mask_w"], cw * cw)
+        l_s, lg_s = self._branch(mix_input(b["ulb_s"], None, None), comp["pseudo_label_w"], comp["mask_w"], H_CW2, "s")
         self._last_branch = False
         if lq is not None:
-            self._forward(self.model, mix_input(lq, None, None), False)
+            self._forward(self.model, mix_input(lq, None, None), False, "lq")
         # 5. data-parallel gradient reduction (averaging folded into the optimiser's grad_scale)
-        gscale = 1.0
         if self.dp is not None:
-            gscale = self.dp.finish_step(self.opt)
+            self.dp.finish_step(self.opt)
         for i, p in enumerate(self.params):
             self.opt.set_has_grad(i, id(p) in self._touched)
-        # 6. fused SGD + EMA, then the reference's lr schedule (train.py:854-858)
-        alpha = min(1 - 1 / (it + 1), self.ema_decay)
-        self.opt.step(lr=self.lr, alpha=alpha, grad_scale=gscale)
-        self.lr = self.base_lr * (1.0 - it / self.max_iterations) ** 0.9
-        self.iter_num = it + 1
-        loss = l_sup[0] + cw * (l_ul[0] + l_lu[0] + cw * l_s[0])
+        # 6. fused SGD + EMA (lr, alpha, gradient scale from the hyper block)
+        self.opt.step(hyper=self.hyper)
+        cw_t = self.hyper[H_CW]
+        loss = l_sup[0] + cw_t * (l_ul[0] + l_lu[0] + cw_t * l_s[0])
         out = dict(comp)
         if self.hardness_mode is not None:
             out["hardness"], out["lq_idx"], out["stu_tea_dice"] = hardness(comp["stu_pseudo_label"], comp["pseudo_label"], self.hardness_mode, self.first_epoch)
-        out.update(loss=loss, sup_loss=l_sup[0], unsup_loss_ul=l_ul[0], unsup_loss_lu=l_lu[0], unsup_loss_s=l_s[0], consistency_weight=cw)
+        out.update(loss=loss, sup_loss=l_sup[0], unsup_loss_ul=l_ul[0], unsup_loss_lu=l_lu[0], unsup_loss_s=l_s[0])
         if keep_logits:
             out["logits"] = dict(t1=t1, t2=t2, t3=t3, s0=s0, lb=lg_lb, ul=lg_ul, lu=lg_lu, s=lg_s)
+        self._domains = None
         return out
 
 
