@@ -27,12 +27,18 @@ class Feature:
 class _Program(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, program, training, need_grad, x, *params):
+    def forward(ctx, program, training, need_grad, precision, x, *params):
         ectx = E.Ctx(training, need_grad, bn_sync=BN_SYNC)
         ectx.bn_world = BN_WORLD
-        a = E.input_nchw(x)
-        a.needs_grad = bool(need_grad and x.requires_grad)
-        outs = program(ectx, a)
+        ctx.precision = precision
+        with E.precision_scope(precision):
+            a = E.input_nchw(x)
+            a.needs_grad = bool(need_grad and x.requires_grad)
+            outs = program(ectx, a)
+            return _Program._finish_forward(ctx, ectx, outs, params, a)
+
+    @staticmethod
+    def _finish_forward(ctx, ectx, outs, params, a):
         results, items, nondiff = [], [], []
         for o in outs:
             if isinstance(o, tuple):                      # (logits, head backward)
@@ -57,20 +63,21 @@ class _Program(torch.autograd.Function):
         if ctx.ectx is None:
             raise RuntimeError("backward through a ustrun program twice (the saved activations were released)")
         sink = E.GradSink()
-        for (kind, obj), g in zip(ctx.items, grads):
-            if g is None or kind == "none":
-                continue
-            if kind == "head":
-                obj(g, sink)
-            else:
-                obj.g = E.input_nchw(g)
-        ctx.ectx.backward(sink)
-        gx = None
-        if ctx.input_act.needs_grad and ctx.input_act.g is not None:
-            gx = E.to_nchw(ctx.input_act.g)
+        with E.precision_scope(ctx.precision):
+            for (kind, obj), g in zip(ctx.items, grads):
+                if g is None or kind == "none":
+                    continue
+                if kind == "head":
+                    obj(g, sink)
+                else:
+                    obj.g = E.input_nchw(g)
+            ctx.ectx.backward(sink)
+            gx = None
+            if ctx.input_act.needs_grad and ctx.input_act.g is not None:
+                gx = E.to_nchw(ctx.input_act.g)
         out = tuple(sink.fresh.get(id(p)) for p in ctx.params)
         ctx.ectx = None                                   # release saved activations
-        return (None, None, None, gx) + out
+        return (None, None, None, None, gx) + out
 
 
 def run_program(module, program, x, training=None):
@@ -81,4 +88,4 @@ def run_program(module, program, x, training=None):
     params = tuple(module.parameters())
     training = module.training if training is None else training
     need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
-    return _Program.apply(program, training, need_grad, x, *params)
+    return _Program.apply(program, training, need_grad, E.tier_a_precision(), x, *params)

@@ -194,8 +194,9 @@ class DataParallel:
         dist.all_reduce(t, group=self.group)
 
     def broadcast_parameters(self, tensors):
+        """Rank 0's tensors to every rank (called by SSLTrainer at attach time: weights and BatchNorm buffers of both models)."""
         for t in tensors:
-            dist.broadcast(t, src=0, group=self.group)
+            dist.broadcast(t.data if hasattr(t, "data") else t, src=0, group=self.group)
 
     # -- hooks called by SSLTrainer ----------------------------------------------------------
     def begin_step(self, opt):

@@ -21,6 +21,9 @@ import torch
 from . import _lib as L
 
 _PRECISION = os.environ.get("USTRUN_PRECISION", "bf16")
+# explicit = chosen by USTRUN_PRECISION or set_precision().  Otherwise the Tier-A bridge follows the caller's autocast state
+# (train.py --amp 1: autocast -> bf16 storage; --amp 0: no autocast -> the fp32 validation mode), the fused step uses bf16.
+_PRECISION_EXPLICIT = "USTRUN_PRECISION" in os.environ
 _FORCE_SIMT = os.environ.get("USTRUN_FORCE_SIMT", "0") == "1"
 LAUNCHES = 0          # C-ABI calls issued
 KERNELS = 0           # kernels those calls launched (bench.py reports it as gpu_launches)
@@ -30,10 +33,35 @@ _KERNELS_PER_CALL = {"ustrun_conv_wgrad": 2, "ustrun_convT2x2_wgrad": 2, "ustrun
 
 
 def set_precision(mode: str) -> None:
-    global _PRECISION
+    global _PRECISION, _PRECISION_EXPLICIT
     if mode not in ("bf16", "fp32"):
         raise ValueError("precision must be 'bf16' or 'fp32'")
     _PRECISION = mode
+    _PRECISION_EXPLICIT = True
+
+
+class precision_scope:
+    """Temporarily run engine ops in ``mode`` (None: leave as is)."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        global _PRECISION
+        self.prev = _PRECISION
+        if self.mode is not None:
+            _PRECISION = self.mode
+
+    def __exit__(self, *exc):
+        global _PRECISION
+        _PRECISION = self.prev
+
+
+def tier_a_precision() -> str:
+    """Precision of a module call through the autograd bridge (Tier A)."""
+    if _PRECISION_EXPLICIT:
+        return _PRECISION
+    return "bf16" if torch.is_autocast_enabled("cuda") else "fp32"
 
 
 def get_precision() -> str:

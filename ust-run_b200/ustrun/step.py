@@ -118,6 +118,11 @@ class SSLTrainer:
         self.dp = dp
         self.forward_kwargs = forward_kwargs or {}
         self.params = list(model.parameters())
+        if dp is not None and getattr(dp, "world", 1) > 1 and getattr(dp, "broadcast_at_attach", True):
+            # every rank must start from rank 0's weights AND BatchNorm buffers (the reference seeds one process; here each
+            # rank constructs its own modules): one broadcast per tensor, once
+            with torch.no_grad():
+                dp.broadcast_parameters([t for m in (model, ema_model) for t in list(m.parameters()) + list(m.buffers())])
         self.opt = FusedSGDEMA(self.params, list(ema_model.parameters()), momentum=momentum, weight_decay=weight_decay)
         self._touched = set()
         self._last_branch = False
@@ -213,6 +218,8 @@ class SSLTrainer:
         if "domain_lb" in batch or "domain_ulb" in batch:
             domains = step_domains(int(batch["domain_lb"]), int(batch["domain_ulb"]))
         tensors = {k: v for k, v in batch.items() if isinstance(v, torch.Tensor)}
+        if "mix_ratio" in batch and "mix_ratio" not in tensors:       # host floats (train.py:180) -> one float64 per sample
+            tensors["mix_ratio"] = torch.as_tensor(batch["mix_ratio"], dtype=torch.float64)
         key = None
         if self.use_graph:
             dom_key = None if domains is None else tuple(domains[t][0] for t in STEP_DOMAIN_TAGS)
