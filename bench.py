@@ -157,7 +157,9 @@ def run_ours(args):
     student, teacher = make_models(model_name, c, k)
     student, teacher = student.cuda().train(), teacher.cuda().train()
     use_graph = args.graph == "on" or (args.graph == "auto" and (dp is None or dp.graph_safe) and args.workload != "cfg5")
-    trainer = SSLTrainer(student, teacher, n_classes=k, branch=branch, base_lr=0.03, max_iterations=60000, threshold=0.95, dp=dp, use_graph=use_graph)
+    lanes = args.lanes if args.lanes > 0 else (1 if (dp is not None or args.workload == "cfg5") else 4)
+    trainer = SSLTrainer(student, teacher, n_classes=k, branch=branch, base_lr=0.03, max_iterations=60000, threshold=0.95, dp=dp, use_graph=use_graph,
+                         lanes=lanes)
     trainer.iter_num = 30000                      # mid-training: consistency weight 1.0, alpha 0.99
     host = S.synthetic_batch(c, k, H, W, Bl, Bu, seed=1337 + rank, branch=branch)
     host["lb_mask"] = host["lb_mask"].to(torch.uint8)
@@ -208,6 +210,7 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()        # the user reads the loss every step
         return out
 
+    dp_parity = dp_parity_record(args, dp, rank, world) if (world > 1 and not args.no_dp_parity) else None
     # one cudaMalloc up front instead of ~40 during the first 20 steps (cfg5 needs > 100 GB of activations + workspaces);
     # graph mode gives the eager pool back before capturing, so it only needs a small reservation
     pool = E.reserve_pool(fraction=(0.6 if args.workload == "cfg5" else 0.5) if not use_graph else 0.1, cap=160 << 30)
@@ -296,13 +299,62 @@ def run_ours(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"{args.workload}: {model_name} {c}x{H}x{W}, {k} classes, {Bl}+{Bu} per GPU, {branch} branch, SSL step",
                        "global_batch": imgs, "parallelism": f"dp{world}", "l2": "working set (GBs of activations per step) >> 126 MB L2; no flush needed", "pool_reserved_gib": round(pool / 2**30, 1),
-                       "cuda_graph": bool(use_graph), "dsbn_domains": list(DSBN_DOMAINS) if dsbn else None,
+                       "cuda_graph": bool(use_graph), "lanes": trainer.lanes, "dsbn_domains": list(DSBN_DOMAINS) if dsbn else None,
                        "sync_bn": (False if (world == 1 or args.no_sync_bn) else ("peer" if dp is not None and dp.peer is not None else "nccl"))},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "parity": parity}
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "parity": parity,
+            "dp_parity": dp_parity}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def dp_parity_record(args, dp, rank, world):
+    """Pre-timing data-parallel parity step (N > 1): `world` ranks x (2+2) images through the DataParallel step (NCCL gradient
+    all-reduce, cross-rank BatchNorm statistics, global CE/Dice sums) against ONE process stepping on the concatenated batch
+    (rank 0, hooks detached) from the same seeded weights: step-0 loss and the updated student weights.  Both sides are this
+    repo's sm_100a step; what is checked is that G ranks x B images == one device with G*B images."""
+    import torch
+    import torch.distributed as dist
+    from ustrun import bridge
+    from ustrun import synth as S
+    from ustrun.step import SSLTrainer
+    model_name, c, k, H, W, _, _, branch = WORKLOADS[args.workload]
+    B = 2
+    dsbn = model_name.endswith("_dsbn3")
+    extra = dict(domain_lb=DSBN_DOMAINS[0], domain_ulb=DSBN_DOMAINS[1]) if dsbn else {}
+    full = S.synthetic_batch(c, k, H, W, B * world, B * world, seed=4242, branch=branch)
+    sl = slice(rank * B, (rank + 1) * B)
+    local_b = {kk: (v[sl] if kk in ("lb_x", "lb_mask", "ulb_w", "ulb_s", "move_transx", "box", "choice") else v) for kk, v in full.items()}
+    s_dp, t_dp = make_models(model_name, c, k)
+    tr = SSLTrainer(s_dp.cuda().train(), t_dp.cuda().train(), n_classes=k, branch=branch, max_iterations=60000, threshold=0.6, dp=dp)
+    tr.iter_num = 30000
+    out = tr.step({**{kk: v.cuda() for kk, v in local_b.items()}, **extra})
+    loss_dp = float(out["loss"])
+    torch.cuda.synchronize()
+    rec = None
+    if rank == 0:
+        saved = (bridge.BN_SYNC, bridge.BN_WORLD)
+        bridge.BN_SYNC, bridge.BN_WORLD = None, 1
+        try:
+            s_1, t_1 = make_models(model_name, c, k)
+            tr1 = SSLTrainer(s_1.cuda().train(), t_1.cuda().train(), n_classes=k, branch=branch, max_iterations=60000, threshold=0.6)
+            tr1.iter_num = 30000
+            out1 = tr1.step({**{kk: v.cuda() for kk, v in full.items()}, **extra})
+            loss_1 = float(out1["loss"])
+            cat = lambda m: torch.cat([q.detach().double().flatten() for q in m.parameters()])
+            w_dp, w_1 = cat(tr.model), cat(tr1.model)
+            rec = {"what": f"{world} ranks x (2+2) images (data-parallel step) vs one process on the concatenated {2 * B * world}-image batch, same seeded weights, {args.precision}",
+                   "loss_dp": loss_dp, "loss_single": loss_1, "loss_rel_err": abs(loss_dp - loss_1) / abs(loss_1),
+                   "student_weights_rel_diff_after_step": float((w_dp - w_1).norm() / w_1.norm()),
+                   "masks_identical": bool(torch.equal(out["mask_w"], out1["mask_w"][sl]))}
+            del s_1, t_1, tr1, out1
+        finally:
+            bridge.BN_SYNC, bridge.BN_WORLD = saved
+    dist.barrier()
+    del tr, s_dp, t_dp, out
+    torch.cuda.empty_cache()
+    return rec
 
 
 def oracle_models(model_name, c, k, device="cpu"):
@@ -442,7 +494,9 @@ def main():
     ap.add_argument("--sync-bn", default="auto", choices=["auto", "peer", "nccl"], help="cross-rank BN statistics: fused peer-memory kernel or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-cuDNN baseline / parity leg (N=1)")
+    ap.add_argument("--no-dp-parity", action="store_true", help="skip the pre-timing data-parallel parity step (N>1)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the step as one CUDA graph (auto: single GPU, not cfg5)")
+    ap.add_argument("--lanes", type=int, default=0, help="CUDA streams the independent forwards / loss branches of a step are spread over (0: auto = 4 on one GPU)")
     ap.add_argument("--ref-budget", type=float, default=420.0, help="--impl reference: seconds of CPU time the whole run may take")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -89,7 +89,24 @@ int ustrun_bn_reduce_partials(const float* partials, int nparts, int C, float* s
 int ustrun_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
                        const float* conv_bias, float* running_mean, float* running_var, long long* num_batches_tracked,
                        float momentum, float eps, int training, float* scale, float* shift, float* mean, float* rstd,
-                       void* stream);
+                       float* stat_out, void* stream);
+/* Deferred running statistics (multi-lane step: independent forwards of one step run concurrently, the running statistics
+ * must still be updated in the reference's forward order, train.py:643-647,668,699-702,740).  ustrun_bn_finalize with
+ * stat_out != NULL (and running_* / nbt NULL) writes the batch statistics {mean + conv bias, unbiased variance} to
+ * stat_out[2][C] instead of updating in place; ustrun_bn_running_update then applies, for n BatchNorm layers in ONE launch,
+ * the slots named by `mask` in increasing slot order with the same arithmetic as the in-place update (bit-identical), and
+ * adds popcount(mask) to num_batches_tracked.  stats: float[slots][2][C] of that layer. */
+typedef struct {
+  float* running_mean;
+  float* running_var;
+  long long* nbt;        /* num_batches_tracked or NULL */
+  const float* stats;    /* [slot][2][C] */
+  int C;
+  unsigned int mask;     /* bit s: slot s holds a forward of this step */
+  float momentum;
+  int pad;
+} ustrun_bn_update_t;
+int ustrun_bn_running_update(const ustrun_bn_update_t* table, int n, int Cmax, void* stream);
 /* y = act(x*scale+shift); optional 2x2 max-pooled copy (nn.MaxPool2d(2): unet_parts.py:34, unet.py:45) */
 int ustrun_bn_act_fwd(const void* x, int ldx, const float* scale, const float* shift, int act, void* y, int ldy,
                       void* pooled, int ldp, int dtype, int B, int H, int W, int C, void* stream);
@@ -98,6 +115,8 @@ int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const f
                          const float* scale, const float* shift, int act, int dtype, long long npix, int C,
                          float* partials, int* nparts_host, void* stream);
 /* dgamma/dbeta (+)= param_grad_scale * (sum g' xhat, sum g'); coef[3][C] = (gamma*rstd, sum g'/count, sum g' xhat/count).
+ * dgamma / dbeta / coef are each nullable (the multi-lane step computes coef on the lane's stream and accumulates the
+ * parameter gradients with a second call on the weight-gradient stream, keeping the accumulation order of the branches).
  * With cross-rank statistics the sums are global: pass param_grad_scale = 1/world so that the later
  * gradient all-reduce (a sum over ranks) yields the global dgamma/dbeta exactly once. */
 int ustrun_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* rstd,

@@ -144,7 +144,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     results = {}
-    out = os.path.join(ROOT, "gpurun_out", "parity_fullsize.json")
+    out = os.path.join(ROOT, "gpurun_out", os.environ.get("USTRUN_PARITY_OUT", "parity_fullsize.json"))
     os.makedirs(os.path.dirname(out), exist_ok=True)
     for n in names:
         try:

@@ -102,7 +102,8 @@ def test_sync_bn_statistics():
 
 def _dp_step_case(rank, world):
     """Each rank: oracle loss/grad on its half of the batch -> DataParallel hooks (begin_step,
-    on_grad_requested in backward order during the last branch, finish_step) -> averaged gradient."""
+    on_grad_done in backward order during the last branch -- each AFTER its gradient was written, with a bucket size that
+    puts single tensors into their own buckets, the case the round-1 advisor flagged -- finish_step) -> averaged gradient."""
     from oracle import ssl_step_ref as S
     from oracle import unet_ref as U
     from ustrun.dp import DataParallel
@@ -132,11 +133,13 @@ def _dp_step_case(rank, world):
     loss.backward()
     opt = FakeOpt(plist)
     assert DataParallel(sync_bn=False, global_loss=True).finish_step.__name__ == 'finish_step'
-    dp = DataParallel(sync_bn=False, global_loss=False, bucket_bytes=4096)     # per-rank losses -> averaged gradients
+    dp = DataParallel(sync_bn=False, global_loss=False, bucket_bytes=64)       # per-rank losses -> averaged gradients
     dp.begin_step(opt)
+    assert len(dp.buckets.ranges) > len(plist) // 2
     for i in reversed(range(len(plist))):
-        dp.on_grad_requested(plist[i], last_branch=True)
         opt.view(i).copy_(plist[i].grad)
+        dp.on_grad_done(plist[i], last_branch=True)          # the bucket may go NOW: its gradient must already be in place
+    assert all(dp.buckets.launched), "every bucket was launched by its last member"
     scale = dp.finish_step(opt)
     assert scale == 0.5
     return opt.flat_grad * scale, [p.grad.clone() for p in plist], opt.offsets

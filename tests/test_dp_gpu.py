@@ -1,0 +1,85 @@
+"""Data-parallel code path on ONE GPU (the driver's GPU tier has a single device): a world-size-1 NCCL process group drives
+``ustrun.dp.DataParallel`` end to end -- gradient buckets on the communication stream (tiny buckets: one tensor each),
+global-loss partial sums, and the PEER-MEMORY BatchNorm finalize kernels of csrc/peer_bn.cu (symmetric-memory buffer, flags,
+sequence numbers; with one rank the cross-rank sum has a single term) -- and must reproduce the plain single-GPU step.
+Multi-rank parity (2 ranks == one process on the concatenated batch, incl. DSBN) is tools/dp_check.py under
+``gpurun --gpus 2`` and bench.py's ``dp_parity`` record; the host logic runs under gloo in tests/test_dp_cpu.py."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.fixture(scope="module")
+def nccl_world1():
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()), RANK="0", WORLD_SIZE="1")
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    yield
+    dist.destroy_process_group()
+
+
+def _pair(kind, **kw):
+    torch.manual_seed(1337)
+    if kind == "a":
+        from networks.unet_model import UNet
+        s, t = UNet(1, 2, **kw), UNet(1, 2, **kw)
+    else:
+        from networks.unet import UNet
+        s, t = UNet(3, 2, **kw), UNet(3, 2, **kw)
+    t.load_state_dict(s.state_dict())
+    for p in t.parameters():
+        p.detach_()
+    return s.cuda().train(), t.cuda().train()
+
+
+@pytest.mark.parametrize("kind,sync", [("a", "peer"), ("a", "nccl"), ("b_dsbn", "peer")])
+def test_world1_data_parallel_equals_plain_step(nccl_world1, kind, sync):
+    from ustrun import bridge
+    from ustrun import synth as S
+    from ustrun.dp import DataParallel
+    from ustrun.step import SSLTrainer
+    dsbn = kind == "b_dsbn"
+    kw = dict(norm="dsbn", num_domains=3) if dsbn else {}
+    c = 3 if dsbn else 1
+    extra = dict(domain_lb=1, domain_ulb=2) if dsbn else {}
+    batches = [{kk: v.cuda() for kk, v in S.synthetic_batch(c, 2, 64, 64, 2, 2, seed=30 + i).items()} for i in range(3)]
+    s0, t0 = _pair(kind[0], **kw)
+    plain = SSLTrainer(s0, t0, n_classes=2, threshold=0.6)
+    ref = [plain.step({**b, **extra})["loss"].clone() for b in batches]
+    s1, t1 = _pair(kind[0], **kw)
+    try:
+        dp = DataParallel(sync_bn=sync, global_loss=True, bucket_bytes=256, force=True)
+    except Exception as e:                                   # symmetric memory not available for a 1-rank group on this box
+        if sync == "peer":
+            pytest.skip(f"peer-memory buffers unavailable: {type(e).__name__}: {e}")
+        raise
+    try:
+        assert (dp.peer is not None) == (sync == "peer")
+        tr = SSLTrainer(s1, t1, n_classes=2, threshold=0.6, dp=dp)
+        got = [tr.step({**b, **extra})["loss"].clone() for b in batches]
+        torch.cuda.synchronize()
+        if dp.peer is not None:
+            dp.peer.check()
+            assert dp.peer.seq > 100                          # every BatchNorm layer of every pass went through the peer kernels
+    finally:
+        dp.close()
+        assert bridge.BN_SYNC is None
+    for a, b in zip(got, ref):
+        assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b)), (float(a), float(b))
+    for p, q in zip(s1.parameters(), s0.parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+    for (n, a), (_, b) in zip(s1.named_buffers(), s0.named_buffers()):
+        assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-7), n

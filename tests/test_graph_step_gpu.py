@@ -99,3 +99,37 @@ def test_trainer_state_dict_roundtrip():
     assert tr2.iter_num == tr.iter_num and tr2.lr == tr.lr
     for p, q in zip(s.parameters(), s2.parameters()):
         assert torch.equal(p, q)
+
+
+@pytest.mark.parametrize("kind,c,k,hw,branch,lanes,graph,dsbn", [("a", 1, 2, 64, "softmax", 2, False, False), ("a", 1, 2, 64, "softmax", 4, True, False),
+                                                                  ("b", 3, 2, 64, "sigmoid", 4, True, False), ("b", 3, 2, 48, "softmax", 3, True, True)])
+def test_multi_lane_step_is_bit_identical(kind, c, k, hw, branch, lanes, graph, dsbn):
+    """lanes > 1 runs the independent forwards / loss branches of a step concurrently on several CUDA streams.  BatchNorm
+    running statistics are logged per forward and applied in the reference's order (ustrun_bn_running_update), parameter
+    gradients accumulate on the one weight-gradient stream in program order: every tensor of the step must equal the
+    single-lane step bit for bit -- losses, planes, student / teacher weights, running statistics, num_batches_tracked."""
+    from ustrun import synth as S
+    from ustrun.step import SSLTrainer
+    kw = dict(norm="dsbn", num_domains=3) if dsbn else {}
+    runs = []
+    for nl, ug in ((1, False), (lanes, graph)):
+        s, t = _pair(kind, c, k, **kw)
+        tr = SSLTrainer(s, t, n_classes=k, branch=branch, max_iterations=400, threshold=0.6, use_graph=ug, lanes=nl)
+        tr.iter_num = 100
+        losses, planes = [], []
+        for i in range(6):
+            b = {kk: v.cuda() for kk, v in S.synthetic_batch(c, k, hw, hw, 2, 2, seed=80 + i, branch=branch).items()}
+            if dsbn:
+                b.update(domain_lb=i % 2, domain_ulb=2)        # two signatures alternate: two graphs, two descriptor tables
+            out = tr.step(b, lq=b["ulb_w"][:1].contiguous())
+            losses.append(out["loss"].detach().clone())
+            planes.append(out["mask_w"].detach().clone())
+        torch.cuda.synchronize()
+        runs.append((losses, planes, [p.detach().clone() for p in s.parameters()] + [p.detach().clone() for p in t.parameters()],
+                     {n: b_.detach().clone() for n, b_ in list(s.named_buffers()) + [("t." + n, v) for n, v in t.named_buffers()]}, tr))
+    (l0, p0, w0, b0, tr0), (l1, p1, w1, b1, tr1) = runs
+    assert tr1.lanes == lanes and len(tr1._lane_streams) >= 2
+    for a, b in zip(l0 + p0 + w0, l1 + p1 + w1):
+        assert torch.equal(a, b)
+    for n in b0:
+        assert torch.equal(b0[n], b1[n]), n

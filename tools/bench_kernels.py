@@ -93,7 +93,7 @@ report("bn_bwd_apply", timeit(lambda: E._call("ustrun_bn_bwd_apply", G.ptr, 64, 
 report("maxpool_bwd (+skip add)", timeit(lambda: E._call("ustrun_maxpool_bwd", y.ptr, 64, pooled.ptr, 64, G.ptr, 64, raw.ptr, 64, L.BF16, B, H, H, 64, S())), bytes_=3.25 * nb16)
 sc4 = torch.empty(4 * 64, device="cuda"); pr = torch.rand(148 * 128, device="cuda")
 gam = torch.ones(64, device="cuda"); rm = torch.zeros(64, device="cuda"); rv = torch.ones(64, device="cuda"); nbt = torch.zeros(1, dtype=torch.int64, device="cuda")
-report("bn_finalize (148 partial rows)", timeit(lambda: E._call("ustrun_bn_finalize", E._ptr(pr), 148, 64, float(npx), E._ptr(gam), E._ptr(rm), None, E._ptr(rm), E._ptr(rv), E._ptr(nbt), 0.1, 1e-5, 1, E._ptr(sc4[:64]), E._ptr(sc4[64:128]), E._ptr(sc4[128:192]), E._ptr(sc4[192:]), S())))
+report("bn_finalize (148 partial rows)", timeit(lambda: E._call("ustrun_bn_finalize", E._ptr(pr), 148, 64, float(npx), E._ptr(gam), E._ptr(rm), None, E._ptr(rm), E._ptr(rv), E._ptr(nbt), 0.1, 1e-5, 1, E._ptr(sc4[:64]), E._ptr(sc4[64:128]), E._ptr(sc4[128:192]), E._ptr(sc4[192:]), None, S())))
 # ---- step kernels ----
 C = 2
 t = [torch.randn(B, C, H, H, device="cuda") * 3 for _ in range(4)]

@@ -13,6 +13,7 @@ from ustrun import engine as E
 from ustrun.step import SSLTrainer
 from ustrun.dp import DataParallel
 from networks.unet_model import UNet
+from networks.unet import UNet as UNetB
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -20,12 +21,19 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     precision = os.environ.get("USTRUN_PRECISION", "fp32")
     E.set_precision(precision)
-    c, k, hw, B = 1, 2, 64, 2
+    # USTRUN_DP_MODEL=b_dsbn: networks/unet.py UNet(norm='dsbn', num_domains=3) with per-forward domain labels -- the cross-rank
+    # statistics then belong to the selected domain's BatchNorm on every rank (BASELINE.json configs[2])
+    dsbn = os.environ.get("USTRUN_DP_MODEL", "a") == "b_dsbn"
+    c, k, hw, B = (3, 2, 64, 2) if dsbn else (1, 2, 64, 2)
+    extra = dict(domain_lb=0, domain_ulb=2) if dsbn else {}
     full = S.synthetic_batch(c, k, hw, hw, B * world, B * world, seed=1337)
     full["choice"] = full["choice"] % (B * world)
     def models():
         torch.manual_seed(1337)
-        s, t = UNet(c, k), UNet(c, k)
+        if dsbn:
+            s, t = UNetB(c, k, norm="dsbn", num_domains=3), UNetB(c, k, norm="dsbn", num_domains=3)
+        else:
+            s, t = UNet(c, k), UNet(c, k)
         t.load_state_dict(s.state_dict())
         for p in t.parameters(): p.detach_()
         return s.cuda().train(), t.cuda().train()
@@ -36,7 +44,7 @@ def main():
     s_dp, t_dp = models()
     tr = SSLTrainer(s_dp, t_dp, n_classes=k, threshold=0.6, dp=dp)
     tr.iter_num = 3000
-    outs = [tr.step({kk: v.cuda() for kk, v in local_batch.items()}) for _ in range(2)]
+    outs = [tr.step({**{kk: v.cuda() for kk, v in local_batch.items()}, **extra}) for _ in range(2)]
     torch.cuda.synchronize()
     if dp.peer is not None:
         dp.peer.check()
@@ -47,7 +55,7 @@ def main():
     s_1, t_1 = models()
     tr1 = SSLTrainer(s_1, t_1, n_classes=k, threshold=0.6)
     tr1.iter_num = 3000
-    outs1 = [tr1.step({kk: v.cuda() for kk, v in full.items()}) for _ in range(2)]
+    outs1 = [tr1.step({**{kk: v.cuda() for kk, v in full.items()}, **extra}) for _ in range(2)]
     torch.cuda.synchronize()
     def rel(a, b): return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
     worst = max(rel(p, q) for p, q in zip(s_dp.parameters(), s_1.parameters()))
@@ -58,7 +66,7 @@ def main():
     gathered = [torch.zeros(1, device="cuda") for _ in range(world)]
     dist.all_gather(gathered, torch.tensor([worst], device="cuda"))
     if rank == 0:
-        print(f"dp_check world={world} precision={precision}: loss rel diff per step {dl}, student weights {worst:.2e} (all ranks {[float(g) for g in gathered]}), "
+        print(f"dp_check world={world} precision={precision} model={'unet_b dsbn x3' if dsbn else 'unet_a'}: loss rel diff per step {dl}, student weights {worst:.2e} (all ranks {[float(g) for g in gathered]}), "
               f"teacher {worst_t:.2e}, running stats {worst_rs:.2e}, step-0 masks identical {same}")
         cat = lambda m: torch.cat([q.detach().double().flatten() for q in m.parameters()])
         allw = rel(cat(s_dp), cat(s_1))

@@ -26,12 +26,13 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--lanes", type=int, default=1)
     a = ap.parse_args()
     model_name, c, k, H, W, Bl, Bu, branch = B.WORKLOADS[a.workload]
     E.set_precision(a.precision)
     student, teacher = B.make_models(model_name, c, k)
     student, teacher = student.cuda().train(), teacher.cuda().train()
-    tr = SSLTrainer(student, teacher, n_classes=k, branch=branch, max_iterations=60000, use_graph=a.graph)
+    tr = SSLTrainer(student, teacher, n_classes=k, branch=branch, max_iterations=60000, use_graph=a.graph, lanes=a.lanes)
     tr.iter_num = 30000
     host = S.synthetic_batch(c, k, H, W, Bl, Bu, seed=1337, branch=branch)
     dev = {kk: v.cuda() for kk, v in host.items()}

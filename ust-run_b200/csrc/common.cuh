@@ -109,6 +109,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// running <- (1 - momentum) * running + momentum * batch, with the rounding points pinned (no FMA contraction) so that the
+// in-place update (k_bn_finalize, k_bn_finalize_peer) and the deferred one (k_bn_running_update) are bit-identical
+__device__ __forceinline__ float bn_running(float running, float batch, float momentum) {
+  return __fadd_rn(__fmul_rn(1.f - momentum, running), __fmul_rn(momentum, batch));
+}
+
 // activation codes shared with the host side
 __device__ __forceinline__ float act_fwd(float y, int act) {
   if (act == USTRUN_ACT_RELU) return y > 0.f ? y : 0.f;

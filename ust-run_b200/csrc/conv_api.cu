@@ -30,6 +30,8 @@ bool mid_wgrad_ok(int Cin, int Cout, int ks, int ldx, int lddy);
 long long mid_wgrad_ws_bytes(int Cin, int Cout, int ks);
 int mid_conv_launch(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout, int ks,
                     float* partials, int* nparts_host, cudaStream_t st);
+bool mid_head_ok(int Cin, int Cout, int ks, int W, int ldx);
+int mid_head_launch(const void* x, int ldx, const void* w, const float* bias, float* y_nchw, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
 int mid_wgrad_launch(const void* dy, int lddy, const void* x, int ldx, float* dw, int accumulate, int B, int H, int W, int Cin, int Cout, int ks,
                      void* workspace, long long ws_bytes, cudaStream_t st);
 
@@ -71,6 +73,8 @@ int ustrun_conv_fwd(int impl, const void* x, int ldx, const void* w_packed, cons
     if (dtype == USTRUN_F32) return narrow_in_launch<float>(x, ldx, w_packed, bias, y, ldy, B, H, W, Cin, Cout, ksize, partials, nparts_host, st);
     return narrow_in_launch<__nv_bfloat16>(x, ldx, w_packed, bias, y, ldy, B, H, W, Cin, Cout, ksize, partials, nparts_host, st);
   }
+  if (dtype == USTRUN_BF16 && out_nchw_f32 && !partials && mid_head_ok(Cin, Cout, ksize, W, ldx))     // UNet-B logits head (3x3): warp-level MMA
+    return mid_head_launch(x, ldx, w_packed, bias, ynchw, B, H, W, Cin, Cout, st);
   if (!partials && narrow_out_ok(Cin, Cout, ksize) && ldx % 8 == 0) {          // logits head
     if (dtype == USTRUN_F32) return narrow_out_launch<float>(x, ldx, w_packed, bias, y, ldy, ynchw, B, H, W, Cin, Cout, ksize, st);
     return narrow_out_launch<__nv_bfloat16>(x, ldx, w_packed, bias, y, ldy, ynchw, B, H, W, Cin, Cout, ksize, st);

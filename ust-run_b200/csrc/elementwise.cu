@@ -146,11 +146,30 @@ __global__ void k_bn_reduce_partials(const float* __restrict__ partials, int npa
   sums[i] = (float)s;
 }
 
+// Deferred running-statistics update (multi-lane step): every train-mode forward of a step wrote its batch statistics
+// (mean incl. the conv bias, unbiased variance) into slot s of stats[slot][2][C]; this kernel applies the slots named by
+// `mask` in increasing slot order = the order of the reference's forwards (train.py:643-647,668,699-702,740), whatever
+// order the forwards actually executed in.  One launch for all BatchNorm layers of a model.
+__global__ void k_bn_running_update(const ustrun_bn_update_t* __restrict__ table) {
+  const ustrun_bn_update_t t = table[blockIdx.x];
+  for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < t.C; c += gridDim.y * blockDim.x) {
+    float rm = t.running_mean[c], rv = t.running_var[c];
+    for (int s = 0; s < 32; ++s)
+      if (t.mask >> s & 1u) {
+        rm = bn_running(rm, t.stats[(size_t)s * 2 * t.C + c], t.momentum);
+        rv = bn_running(rv, t.stats[(size_t)s * 2 * t.C + t.C + c], t.momentum);
+      }
+    t.running_mean[c] = rm;
+    t.running_var[c] = rv;
+  }
+  if (blockIdx.y == 0 && threadIdx.x == 0 && t.nbt) *t.nbt += __popc(t.mask);
+}
+
 __global__ void k_bn_finalize(const float* __restrict__ partials, int nparts, int C, double count,
                               const float* __restrict__ gamma, const float* __restrict__ beta,
                               const float* __restrict__ conv_bias, float* running_mean, float* running_var,
                               long long* nbt, float momentum, float eps, int training, float* scale, float* shift,
-                              float* mean_out, float* rstd_out) {
+                              float* mean_out, float* rstd_out, float* stat_out) {
   // one warp per channel: lanes stride over the partial rows, double accumulation, shuffle reduce
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt) *nbt += 1;
@@ -178,10 +197,16 @@ __global__ void k_bn_finalize(const float* __restrict__ partials, int nparts, in
     shift[c] = b - mf * g * rstd;                    // conv bias cancels in train mode
     mean_out[c] = mf;
     rstd_out[c] = rstd;
-    if (running_mean) {
-      double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mf + cb);
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    if (running_mean || stat_out) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      const float bm = __fadd_rn(mf, cb), bv = (float)unbiased;
+      if (stat_out) {                // deferred: k_bn_running_update applies the step's forwards in the reference's order
+        stat_out[c] = bm;
+        stat_out[C + c] = bv;
+      } else {
+        running_mean[c] = bn_running(running_mean[c], bm, momentum);
+        running_var[c] = bn_running(running_var[c], bv, momentum);
+      }
     }
   } else {
     if (lane != 0) return;
@@ -366,10 +391,12 @@ __global__ void k_bn_bwd_finalize(const float* __restrict__ partials, int nparts
   if (lane != 0) return;
   if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + param_grad_scale * (float)s2;
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + param_grad_scale * (float)s1;
-  float g = gamma ? gamma[c] : 1.f;
-  coef[c] = g * rstd[c];
-  coef[C + c] = (float)(s1 / count);
-  coef[2 * C + c] = (float)(s2 / count);
+  if (coef) {               // nullable: the multi-lane step accumulates the parameter gradients in a second call on the side stream
+    float g = gamma ? gamma[c] : 1.f;
+    coef[c] = g * rstd[c];
+    coef[C + c] = (float)(s1 / count);
+    coef[2 * C + c] = (float)(s2 / count);
+  }
 }
 
 template <typename T>
@@ -681,13 +708,20 @@ int ustrun_bn_reduce_partials(const float* partials, int nparts, int C, float* s
 }
 int ustrun_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
                        const float* conv_bias, float* running_mean, float* running_var, long long* nbt, float momentum,
-                       float eps, int training, float* scale, float* shift, float* mean, float* rstd, void* stream) {
+                       float eps, int training, float* scale, float* shift, float* mean, float* rstd, float* stat_out, void* stream) {
   USTRUN_REQUIRE(C > 0 && scale && shift && mean && rstd, "bn_finalize: bad args");
+  USTRUN_REQUIRE(!stat_out || (training && !running_mean && !running_var && !nbt), "bn_finalize: stat_out replaces the in-place running update");
   USTRUN_REQUIRE(!training || (partials && nparts > 0 && count > 0), "bn_finalize: training needs partials");
   USTRUN_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval needs running stats");
   k_bn_finalize<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, beta, conv_bias, running_mean,
-                                                                   running_var, nbt, momentum, eps, training, scale, shift, mean, rstd);
+                                                                   running_var, nbt, momentum, eps, training, scale, shift, mean, rstd, stat_out);
   return check_launch("bn_finalize");
+}
+int ustrun_bn_running_update(const ustrun_bn_update_t* table, int n, int Cmax, void* stream) {
+  USTRUN_REQUIRE(table && n > 0 && Cmax > 0, "bn_running_update: bad args");
+  dim3 grid(n, ceil_div(Cmax, 256));
+  k_bn_running_update<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
+  return check_launch("bn_running_update");
 }
 int ustrun_bn_act_fwd(const void* x, int ldx, const float* scale, const float* shift, int act, void* y, int ldy, void* pooled,
                       int ldp, int dtype, int B, int H, int W, int C, void* stream) {
@@ -725,7 +759,7 @@ int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const f
 }
 int ustrun_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* rstd, float* dgamma,
                            float* dbeta, int accumulate, float param_grad_scale, float* coef, void* stream) {
-  USTRUN_REQUIRE(partials && nparts > 0 && C > 0 && rstd && coef && count > 0, "bn_bwd_finalize: bad args");
+  USTRUN_REQUIRE(partials && nparts > 0 && C > 0 && rstd && count > 0 && (coef || dgamma || dbeta), "bn_bwd_finalize: bad args");
   k_bn_bwd_finalize<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, rstd, dgamma, dbeta, accumulate, param_grad_scale, coef);
   return check_launch("bn_bwd_finalize");
 }

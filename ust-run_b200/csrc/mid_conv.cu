@@ -57,10 +57,14 @@ struct MidCfg {
   static constexpr size_t smem = (size_t)wfrag_u32 * 4 + (size_t)8 * warp_elems * 2 + (size_t)8 * 2 * COUT * 4;
 };
 
-template <int CIN, int NT, int KS>
+// HEAD = true: the logits head of UNet-B (out1 / seg1: conv3x3 2n -> n_classes + bias, unet.py:182,312).  The output tile is
+// padded to 16 columns (cout_valid <= 16 real classes, zero weights beyond) and leaves as fp32 NCHW class planes -- eight
+// consecutive pixels per store instruction -- instead of a bf16 NHWC tile; no BatchNorm statistics.
+template <int CIN, int NT, int KS, bool HEAD = false>
 __global__ void __launch_bounds__(256)
 k_conv_mid_mma(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias,
-               __nv_bfloat16* __restrict__ y, int ldy, int B, int H, int W, float* __restrict__ partials) {
+               __nv_bfloat16* __restrict__ y, int ldy, int B, int H, int W, float* __restrict__ partials, float* __restrict__ y_nchw = nullptr,
+               int cout_valid = NT * 8) {
   using Cfg = MidCfg<CIN, NT, KS>;
   constexpr int R = Cfg::R, TAPS = Cfg::TAPS, K = Cfg::K, KSTEPS = Cfg::KSTEPS, COUT = Cfg::COUT, CPT = Cfg::CPT;
   constexpr int XW = Cfg::XW, XP = Cfg::XP, SP = Cfg::SP, NCH = Cfg::NCH;
@@ -73,8 +77,9 @@ k_conv_mid_mma(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16
     const int ln = i & 31, j = (i >> 5) % NT, s_ = i / (32 * NT);
     const uint32_t* wr = reinterpret_cast<const uint32_t*>(wp + (size_t)(8 * j + (ln >> 2)) * K + 16 * s_ + 2 * (ln & 3));
     uint32_t* d = wfrag + ((s_ * (NT / 2) + (j >> 1)) * 32 + ln) * 4 + 2 * (j & 1);
-    d[0] = wr[0];
-    d[1] = wr[4];
+    const bool real = !HEAD || (8 * j + (ln >> 2)) < cout_valid;
+    d[0] = real ? wr[0] : 0u;
+    d[1] = real ? wr[4] : 0u;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -83,7 +88,8 @@ k_conv_mid_mma(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16
   float bs[NT][2], ssum[NT][2], ssq[NT][2];
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
-    bs[j][0] = bias ? bias[8 * j + 2 * tig] : 0.f; bs[j][1] = bias ? bias[8 * j + 2 * tig + 1] : 0.f;
+    bs[j][0] = (bias && 8 * j + 2 * tig < cout_valid) ? bias[8 * j + 2 * tig] : 0.f;
+    bs[j][1] = (bias && 8 * j + 2 * tig + 1 < cout_valid) ? bias[8 * j + 2 * tig + 1] : 0.f;
     ssum[j][0] = ssum[j][1] = ssq[j][0] = ssq[j][1] = 0.f;
   }
   const int tiles_w = W >> 4;
@@ -143,6 +149,21 @@ k_conv_mid_mma(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16
       }
     }
     __syncwarp();                                // every lane is done with the slab: reuse it as the output staging tile
+    if constexpr (HEAD) {
+      const long long plane = (long long)H * W;
+      float* o = y_nchw + (long long)b_ * cout_valid * plane + (long long)h_ * W + w0 + g;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int co = 8 * j + 2 * tig + e;
+          if (co < cout_valid) {
+            o[co * plane] = acc[j][e] + bs[j][e];
+            o[co * plane + 8] = acc[j][2 + e] + bs[j][e];
+          }
+        }
+      continue;
+    }
     __nv_bfloat16* st = slab;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -353,6 +374,29 @@ int mid_conv_launch(const void* x, int ldx, const void* w, const float* bias, vo
   if (Cin == 32) return MC(32);
   return MC(64);
 #undef MC
+}
+
+// logits head of UNet-B: conv3x3 (16 | 32 channels -> <= 16 classes) + bias -> fp32 NCHW
+bool mid_head_ok(int Cin, int Cout, int ks, int W, int ldx) {
+  return mid_mode() > 0 && (Cin == 16 || Cin == 32) && Cout >= 1 && Cout <= 16 && ks == 3 && W % 16 == 0 && ldx % 8 == 0;
+}
+template <int CIN>
+static int mid_head_launch_t(const void* x, int ldx, const void* w, const float* bias, float* y_nchw, int B, int H, int W, int Cout, cudaStream_t st) {
+  const size_t smem = MidCfg<CIN, 2, 3>::smem;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_mid_mma<CIN, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_conv_mid_mma head): %s", cudaGetErrorString(e)); return (int)e; }
+    attr = true;
+  }
+  const long long ntiles = (long long)B * H * (W / 16);
+  long long g = (ntiles + 7) / 8;
+  if (g > 148 * 4) g = 148 * 4;
+  k_conv_mid_mma<CIN, 2, 3, true><<<(int)g, 256, smem, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, bias, nullptr, 0, B, H, W, nullptr, y_nchw, Cout);
+  return check_launch("conv_mid_mma(head)");
+}
+int mid_head_launch(const void* x, int ldx, const void* w, const float* bias, float* y_nchw, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  return Cin == 16 ? mid_head_launch_t<16>(x, ldx, w, bias, y_nchw, B, H, W, Cout, st) : mid_head_launch_t<32>(x, ldx, w, bias, y_nchw, B, H, W, Cout, st);
 }
 
 int launch_wgrad_reduce(const float* ws, int splits, int Mo, int Nin, int taps, float* dw, int accumulate, cudaStream_t st, int swapped);

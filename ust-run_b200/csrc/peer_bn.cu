@@ -95,8 +95,8 @@ __global__ void k_bn_finalize_peer(const float* __restrict__ partials, int npart
   rstd_out[c] = rstd;
   if (running_mean) {
     const double unbiased = count_global > 1.0 ? var * count_global / (count_global - 1.0) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mf + cb);
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    running_mean[c] = bn_running(running_mean[c], __fadd_rn(mf, cb), momentum);
+    running_var[c] = bn_running(running_var[c], (float)unbiased, momentum);
   }
 }
 

@@ -46,7 +46,8 @@ _SIGS = {
     "ustrun_convT2x2_wgrad": [i32, p, i32, p, i32, p, i32, i32, i32, i32, i32, i32, i32, p, i64, p],
     "ustrun_channel_sum": [p, i32, i32, i64, i32, p, i32, p, p],
     "ustrun_bn_reduce_partials": [p, i32, i32, p, p],
-    "ustrun_bn_finalize": [p, i32, i32, f64, p, p, p, p, p, p, f32, f32, i32, p, p, p, p, p],
+    "ustrun_bn_finalize": [p, i32, i32, f64, p, p, p, p, p, p, f32, f32, i32, p, p, p, p, p, p],
+    "ustrun_bn_running_update": [p, i32, i32, p],
     "ustrun_bn_act_fwd": [p, i32, p, p, i32, p, i32, p, i32, i32, i32, i32, i32, i32, p],
     "ustrun_bn_bwd_reduce": [p, i32, p, i32, p, p, p, p, i32, i32, i64, i32, p, ip, p],
     "ustrun_bn_bwd_finalize": [p, i32, i32, f64, p, p, p, p, i32, f32, p, p],

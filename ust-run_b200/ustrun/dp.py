@@ -158,11 +158,13 @@ class DataParallel:
     """Attach to an ``SSLTrainer`` (``dp=`` argument).  ``sync_bn`` installs the cross-rank
     BatchNorm statistics hook used by every conv+BN op."""
 
-    def __init__(self, group=None, bucket_bytes: int = 32 << 20, sync_bn: bool = True, global_loss: bool = True):
+    def __init__(self, group=None, bucket_bytes: int = 32 << 20, sync_bn: bool = True, global_loss: bool = True, force: bool = False):
         assert dist.is_initialized(), "init_process_group first (backend nccl on GPUs, gloo in CPU tests)"
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        # force: run every collective / peer kernel even in a 1-rank group (single-GPU tests of this code path)
+        self.active = self.world > 1 or bool(force)
         self.bucket_bytes = bucket_bytes
         self.buckets: Optional[GradBuckets] = None
         self.branch = 0
@@ -173,7 +175,7 @@ class DataParallel:
         self.global_loss = global_loss
         self.peer = None
         self.graph_safe = False          # per-layer sequence numbers of the peer-BN kernels are launch arguments: no graph replay
-        if sync_bn and self.world > 1:
+        if sync_bn and self.active:
             # sync_bn="peer" (default on GPUs): finalize kernels reduce over NVLink peer memory themselves;
             # sync_bn="nccl": one NCCL all-reduce per layer and pass (validation / CPU tests)
             want_peer = sync_bn == "peer" or (sync_bn is True and torch.cuda.is_available() and dist.get_backend(group) == "nccl")
@@ -206,22 +208,20 @@ class DataParallel:
             self._index = {id(p): i for i, p in enumerate(opt.params)}
         self.buckets.reset()
         self.branch = 0
-        self._last_requested = None
 
     def on_branch_done(self):
         self.branch += 1
 
-    def on_grad_requested(self, param, last_branch: bool):
-        """Called right before a weight-gradient kernel for ``param`` is enqueued: the previously
-        requested tensor's kernel is then already in the stream, so its bucket may go."""
-        if not last_branch or self.world == 1:
+    def on_grad_done(self, param, last_branch: bool):
+        """Called right AFTER the kernel that writes ``param``'s gradient (the last loss branch's contribution) has been
+        enqueued on the current stream: its bucket may be all-reduced once every member has reported, ordered after the
+        streams that produced them (weight gradients: the engine's side stream; BatchNorm / bias gradients: the main one)."""
+        if not last_branch or not self.active:
             return
         cur = torch.cuda.current_stream() if torch.cuda.is_available() else None
-        if self._last_requested is not None:
-            self.buckets.mark(*self._last_requested)
-        self._last_requested = (self._index[id(param)], cur)
+        self.buckets.mark(self._index[id(param)], cur)
 
     def finish_step(self, opt) -> float:
-        if self.world > 1:
+        if self.active:
             self.buckets.flush()
         return 1.0 if self.global_loss else 1.0 / self.world

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -246,9 +247,18 @@ class Act:
 class GradSink:
     """Where weight gradients go.  ``get(param)`` returns (fp32 tensor, accumulate_flag)."""
 
-    def __init__(self, provider: Optional[Callable] = None):
+    def __init__(self, provider: Optional[Callable] = None, done: Optional[Callable] = None):
         self.provider = provider
+        self._done = done
         self.fresh: Dict[int, torch.Tensor] = {}
+
+    def done(self, *params):
+        """The kernel that writes these parameters' gradients has just been enqueued on the CURRENT stream (data-parallel
+        gradient buckets may be all-reduced from here on, ordered after that stream)."""
+        if self._done is not None:
+            for p in params:
+                if p is not None:
+                    self._done(p)
 
     def get(self, param: torch.Tensor):
         if self.provider is not None:
@@ -264,13 +274,19 @@ class GradSink:
 class Ctx:
     """One forward pass: holds the backward tape when gradients are needed."""
 
-    def __init__(self, training: bool, need_grad: bool, bn_sync: Optional[Callable] = None):
+    def __init__(self, training: bool, need_grad: bool, bn_sync: Optional[Callable] = None, stats: Optional["StatLog"] = None,
+                 slot: int = 0, grads_on_side: bool = False):
         self.training = training
         self.need_grad = need_grad
         self.tape: List[Callable] = []
         self.bn_sync = bn_sync           # callable(tensor[2*C]) -> None (in-place cross-rank sum) or None
         self.bn_world = 1
         self.bn_peer = getattr(bn_sync, "peer", None)   # PeerStats: fused finalize + NVLink peer-memory reduction
+        # multi-lane step: BatchNorm running statistics are logged per forward (slot) and applied in the reference's order at
+        # the end of the step; every parameter-gradient accumulation goes to the ONE weight-gradient stream in program order
+        self.stats = stats
+        self.slot = slot
+        self.grads_on_side = grads_on_side
 
     def backward(self, sink: GradSink, join: bool = True):
         """``join=False`` leaves the weight-gradient side stream running (the fused step joins once, before the
@@ -282,6 +298,70 @@ class Ctx:
             join_side_stream()           # weight gradients are complete for whoever runs next on this stream
 
 
+class StatLog:
+    """Deferred BatchNorm running statistics of one step (see ustrun_bn_running_update): ``slot_ptr`` hands the finalize
+    kernel the slot of (layer, forward); ``flush`` applies every layer's logged forwards in slot order with one launch."""
+    SLOTS = 8
+
+    def __init__(self):
+        self.entries: Dict[int, list] = {}        # id(bn) -> [bn, stats tensor [SLOTS][2][C], mask]
+        self._tables: Dict[tuple, tuple] = {}
+
+    def begin_step(self):
+        for e in self.entries.values():
+            e[2] = 0
+
+    def slot_ptr(self, bn, slot: int) -> int:
+        e = self.entries.get(id(bn))
+        if e is None:
+            C = bn.num_features
+            e = self.entries[id(bn)] = [bn, torch.zeros((self.SLOTS, 2, C), dtype=torch.float32, device=bn.running_mean.device), 0]
+        e[2] |= 1 << slot
+        return e[1].data_ptr() + slot * 2 * bn.num_features * 4
+
+    def flush(self):
+        import numpy as np
+        live = [e for e in self.entries.values() if e[2]]
+        if not live:
+            return
+        key = tuple((id(e[0]), e[2], e[0].running_mean.data_ptr()) for e in live)
+        ent = self._tables.get(key)
+        if ent is None:
+            dt = np.dtype([("rm", "<u8"), ("rv", "<u8"), ("nbt", "<u8"), ("stats", "<u8"), ("C", "<i4"), ("mask", "<u4"), ("mom", "<f4"), ("pad", "<i4")])
+            tab = np.zeros(len(live), dtype=dt)
+            for i, (bn, stats, mask) in enumerate(live):
+                tab[i]["rm"], tab[i]["rv"] = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+                tab[i]["nbt"] = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else 0
+                tab[i]["stats"], tab[i]["C"], tab[i]["mask"] = stats.data_ptr(), bn.num_features, mask
+                tab[i]["mom"] = 0.1 if bn.momentum is None else float(bn.momentum)
+            dev = live[0][1].device
+            t = torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).to(dev)
+            ent = self._tables[key] = (t, len(live), max(e[0].num_features for e in live))
+        t, n, cmax = ent
+        _call("ustrun_bn_running_update", _ptr(t), n, cmax, _stream())
+
+
+def collect_packed(*models):
+    """Every PackedConv of the given modules (attributes named ``_pk*``: one object or a list)."""
+    out = []
+    for model in models:
+        for m in model.modules():
+            for name, v in vars(m).items():
+                if name.startswith("_pk"):
+                    out.extend(v if isinstance(v, (list, tuple)) else [v])
+    return [p for p in out if isinstance(p, PackedConv)]
+
+
+def prepack(packed_list):
+    """Refresh the packed weight copies on the CURRENT stream (multi-lane step: before the lanes fork, so that no lane
+    depends on a packing kernel another lane launched).  Only convs that have run before are known."""
+    for pk in packed_list:
+        if pk.last is not None:
+            w = pk.last[0]()
+            if w is not None:
+                pk.get(w, transposed=pk.last[1], need_wd=pk.last[2])
+
+
 # --------------------------------------------------------------------------------------------
 # packed weights (bf16/fp32 [Cout][tap][Cin] forward and [Cin][tap'][Cout] dgrad copies)
 # --------------------------------------------------------------------------------------------
@@ -291,10 +371,13 @@ class PackedConv:
         self.wf = None
         self.wd = None
         self.has_wd = False
+        self.last = None          # (weakref to the weight, transposed, need_wd) of the last get(): what prepack() replays
 
     def get(self, weight: torch.Tensor, transposed=False, need_wd=True):
         """(wf, wd) for ``weight``.  ``need_wd=False`` (no-grad forwards: the teacher never runs a dgrad) packs only the
         forward copy; the dgrad copy is added lazily the first time a caller asks for it."""
+        if self.last is None or self.last[0]() is not weight or (need_wd and not self.last[2]):
+            self.last = (weakref.ref(weight), transposed, bool(need_wd))
         tdt, code = _dt()
         key = (weight.data_ptr(), weight._version, code, getattr(weight, "_ustrun_epoch", 0))
         fresh = key != self.key
@@ -408,6 +491,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
     count = float(x.npix)
     track = bn.track_running_stats and bn.running_mean is not None and training
     peer = ctx.bn_peer if use_batch_stats else None
+    stat_ptr = ctx.stats.slot_ptr(bn, ctx.slot) if (track and ctx.stats is not None and ctx.bn_sync is None) else None
     if use_batch_stats and ctx.bn_sync is not None and peer is None:
         sums = torch.empty(2 * cout, dtype=torch.float32, device=dev)
         _call("ustrun_bn_reduce_partials", _ptr(partials), nparts, cout, _ptr(sums), _stream())
@@ -419,11 +503,11 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
               _ptr(bn.num_batches_tracked) if track else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
               _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), *peer.args(), _stream())
     else:
+      inplace = (track and stat_ptr is None) or not use_batch_stats
       _call("ustrun_bn_finalize", _ptr(partials), nparts, cout, count, _ptr(bn.weight), _ptr(bn.bias), _ptr(conv.bias),
-          _ptr(bn.running_mean) if (track or not use_batch_stats) else None,
-          _ptr(bn.running_var) if (track or not use_batch_stats) else None,
-          _ptr(bn.num_batches_tracked) if track else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
-          1 if use_batch_stats else 0, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _stream())
+          _ptr(bn.running_mean) if inplace else None, _ptr(bn.running_var) if inplace else None,
+          _ptr(bn.num_batches_tracked) if (track and stat_ptr is None) else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
+          1 if use_batch_stats else 0, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), stat_ptr, _stream())
     y = out if out is not None else x.like(cout)
     pooled = Act.new(x.B, x.H // 2, x.W // 2, cout, dtype=x.t.dtype, device=dev) if pool else None
     _profiled("hbm_bn_act", raw.npix * cout * raw.t.element_size() * (2.25 if pool else 2.0), "ustrun_bn_act_fwd", raw.ptr, raw.ld, _ptr(scale), _ptr(shift), act, y.ptr, y.ld, pooled.ptr if pool else None,
@@ -435,6 +519,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
         world = ctx.bn_world if ctx.bn_sync is not None else 1
         bn_sync = ctx.bn_sync
         bn_peer = ctx.bn_peer
+        gos = ctx.grads_on_side and bn_sync is None
 
         def bwd(sink: GradSink):
             G = y.g
@@ -461,9 +546,19 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
                 _call("ustrun_bn_reduce_partials", _ptr(part), n_parts, cout, _ptr(sums), _stream())
                 bn_sync(sums)
                 part, n_parts, cnt = sums, 1, cnt * world
-            if bn_peer is None:
+            if bn_peer is None and gos:
+                # coefficients on this lane's stream; dgamma / dbeta accumulate on the weight-gradient stream, whose program
+                # order (branch after branch) keeps the accumulation order of the single-lane step
+                _call("ustrun_bn_bwd_finalize", _ptr(part), n_parts, cout, cnt, _ptr(bn.weight), _ptr(rstd), None, None, 0, 1.0, _ptr(coef), _stream())
+                def bn_grads_fn(part=part, n_parts=n_parts, cnt=cnt, dg=dg, db=db, acc=1 if (acc_g or acc_b) else 0):
+                    _call("ustrun_bn_bwd_finalize", _ptr(part), n_parts, cout, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db), acc, 1.0, None, _stream())
+                    sink.done(bn.weight, bn.bias)
+                on_side_stream(bn_grads_fn, (part, rstd))
+            elif bn_peer is None:
               _call("ustrun_bn_bwd_finalize", _ptr(part), n_parts, cout, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
                   1 if (acc_g or acc_b) else 0, 1.0 / world if bn_sync is not None else 1.0, _ptr(coef), _stream())
+            if not (bn_peer is None and gos):
+                sink.done(bn.weight, bn.bias)
             draw = raw.like()
             _profiled("hbm_bn_bwd_apply", raw.npix * cout * raw.t.element_size() * 3.0, "ustrun_bn_bwd_apply", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
                   act, draw.ptr, draw.ld, raw.dtype_code, raw.npix, cout, _stream())
@@ -471,9 +566,11 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
                 dbias, acc = sink.get(conv.bias)          # BN removes the mean: d/dbias == 0 exactly
                 if not acc:
                     dbias.zero_()
+                sink.done(conv.bias)
             def wgrad_fn():
                 dw, acc_w = sink.get(conv.weight)
                 _wgrad(draw, x, dw, acc_w, ks)
+                sink.done(conv.weight)
             if not _WGRAD_AFTER_DGRAD:
                 on_side_stream(wgrad_fn, (draw.t, x.t))
             if x.needs_grad:
@@ -505,6 +602,7 @@ def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
     _call("ustrun_convT2x2_fwd", impl, x.ptr, x.ld, _ptr(wf), _ptr(up.bias), out.ptr, out.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream())
     if ctx.need_grad:
         dev = x.t.device
+        gos = ctx.grads_on_side and ctx.bn_sync is None
 
         def bwd(sink: GradSink):
             G = out.g
@@ -516,11 +614,18 @@ def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
                 ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
                 _call("ustrun_convT2x2_wgrad", impl, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code, x.B, x.H, x.W, cin, cout,
                       _ptr(ws), int(nbytes), _stream())
+                sink.done(up.weight)
             on_side_stream(wgrad_fn, (G.t, x.t))
             if up.bias is not None:
-                db, accb = sink.get(up.bias)
-                wsb = torch.empty(L.MAX_PARTS * cout, dtype=torch.float32, device=dev)
-                _call("ustrun_channel_sum", G.ptr, G.ld, G.dtype_code, G.npix, cout, _ptr(db), accb, _ptr(wsb), _stream())
+                def bias_fn():
+                    db, accb = sink.get(up.bias)
+                    wsb = torch.empty(L.MAX_PARTS * cout, dtype=torch.float32, device=dev)
+                    _call("ustrun_channel_sum", G.ptr, G.ld, G.dtype_code, G.npix, cout, _ptr(db), accb, _ptr(wsb), _stream())
+                    sink.done(up.bias)
+                if gos:
+                    on_side_stream(bias_fn, (G.t,))
+                else:
+                    bias_fn()
             if x.needs_grad:
                 gx = Act.new(x.B, x.H, x.W, x.C, dtype=x.t.dtype, device=dev)
                 _call("ustrun_convT2x2_dgrad", impl, G.ptr, G.ld, _ptr(wd), gx.ptr, gx.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream())
@@ -557,6 +662,7 @@ def head_conv(ctx: Ctx, x: Act, conv, packed: PackedConv):
     wf, wd = packed.get(conv.weight, need_wd=ctx.need_grad or conv.weight.requires_grad)
     logits = torch.empty((x.B, cout, x.H, x.W), dtype=torch.float32, device=x.t.device)
     _raw_conv(x, wf, conv.bias, None, ks, out_nchw=logits)
+    gos = ctx.grads_on_side and ctx.bn_sync is None
 
     def bwd(dlogits: torch.Tensor, sink: GradSink):
         dev = x.t.device
@@ -570,11 +676,18 @@ def head_conv(ctx: Ctx, x: Act, conv, packed: PackedConv):
             ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
             _call("ustrun_conv_wgrad", L.SIMT, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code, x.B, x.H, x.W, x.C, cout, ks,
                   _ptr(ws), int(nbytes), _stream())
+            sink.done(conv.weight)
         on_side_stream(wgrad_fn, (G.t, x.t))
         if conv.bias is not None:
-            db, accb = sink.get(conv.bias)
-            wsb = torch.empty(L.MAX_PARTS * cout, dtype=torch.float32, device=dev)
-            _call("ustrun_channel_sum", G.ptr, G.ld, G.dtype_code, G.npix, cout, _ptr(db), accb, _ptr(wsb), _stream())
+            def bias_fn():
+                db, accb = sink.get(conv.bias)
+                wsb = torch.empty(L.MAX_PARTS * cout, dtype=torch.float32, device=dev)
+                _call("ustrun_channel_sum", G.ptr, G.ld, G.dtype_code, G.npix, cout, _ptr(db), accb, _ptr(wsb), _stream())
+                sink.done(conv.bias)
+            if gos:
+                on_side_stream(bias_fn, (G.t,))
+            else:
+                bias_fn()
         if x.needs_grad:
             gx = Act.new(x.B, x.H, x.W, x.C, dtype=x.t.dtype, device=dev)
             nparts = ctypes.c_int(0)
@@ -615,7 +728,7 @@ def batchnorm_only(ctx: Ctx, x: Act, bn):
     _call("ustrun_bn_finalize", _ptr(part), nparts, C, count, _ptr(bn.weight), _ptr(bn.bias), None,
           _ptr(bn.running_mean) if (track or not use_batch) else None, _ptr(bn.running_var) if (track or not use_batch) else None,
           _ptr(bn.num_batches_tracked) if track else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
-          1 if use_batch else 0, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _stream())
+          1 if use_batch else 0, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), None, _stream())
     y = x.like()
     _call("ustrun_bn_act_fwd", x.ptr, x.ld, _ptr(scale), _ptr(shift), L.ACT_NONE, y.ptr, y.ld, None, 0, x.dtype_code, x.B, x.H, x.W, C, _stream())
     if ctx.need_grad:
@@ -640,6 +753,7 @@ def batchnorm_only(ctx: Ctx, x: Act, bn):
             db, a2 = sink.get(bn.bias) if bn.bias is not None else (None, 0)
             _call("ustrun_bn_bwd_finalize", _ptr(parts), n_parts, C, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db), 1 if (a1 or a2) else 0,
                   1.0 / world if bn_sync is not None else 1.0, _ptr(coef), _stream())
+            sink.done(bn.weight, bn.bias)
             if x.needs_grad:
                 gx = x.like()
                 _call("ustrun_bn_bwd_apply", G.ptr, G.ld, x.ptr, x.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),

@@ -29,7 +29,7 @@ def term_forward(logits, target_u8, mask_u8, branch, ce_w=1.0, dice_w=1.0, class
     B, C, H, W = logits.shape
     dev = logits.device
     loss3 = torch.empty(3, dtype=torch.float32, device=dev)
-    if allreduce is not None and world > 1:
+    if allreduce is not None:
         ncols = 3 * C + 1 if branch == "softmax" else 4
         ws = torch.empty(L.MAX_PARTS * ncols, dtype=torch.float32, device=dev)
         sums = torch.empty(ncols, dtype=torch.float32, device=dev)

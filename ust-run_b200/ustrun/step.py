@@ -105,7 +105,7 @@ def step_domains(domain_lb, domain_ulb):
 class SSLTrainer:
     def __init__(self, model, ema_model, n_classes, branch="softmax", base_lr=0.03, max_iterations=30000, threshold=0.95,
                  consistency=1.0, consistency_rampup=200.0, ema_decay=0.99, momentum=0.9, weight_decay=1e-4, dp=None,
-                 forward_kwargs=None, fft_window=0.01, hardness_mode=None, use_graph=False):
+                 forward_kwargs=None, fft_window=0.01, hardness_mode=None, use_graph=False, lanes=1):
         self.model, self.ema_model = model, ema_model
         self.n_classes, self.branch = n_classes, branch
         self.base_lr, self.lr, self.max_iterations = base_lr, base_lr, max_iterations
@@ -118,7 +118,7 @@ class SSLTrainer:
         self.dp = dp
         self.forward_kwargs = forward_kwargs or {}
         self.params = list(model.parameters())
-        if dp is not None and getattr(dp, "world", 1) > 1 and getattr(dp, "broadcast_at_attach", True):
+        if dp is not None and getattr(dp, "active", False) and getattr(dp, "broadcast_at_attach", True):
             # every rank must start from rank 0's weights AND BatchNorm buffers (the reference seeds one process; here each
             # rank constructs its own modules): one broadcast per tensor, once
             with torch.no_grad():
@@ -134,6 +134,15 @@ class SSLTrainer:
         self._hyper_ev = [None] * _HYPER_RING
         self._hyper_slot = 0
         self.use_graph = bool(use_graph)
+        # lanes > 1: the independent forwards of a step (t1 | t2 | t3 | s0, then the loss branches lb | ul | lu | s | lq) are
+        # enqueued round-robin on `lanes` CUDA streams.  Results are bit-identical to lanes = 1: BatchNorm running statistics
+        # are logged per forward and applied in the reference's order at the end of the step (E.StatLog), and every
+        # parameter-gradient accumulation runs on the one weight-gradient stream in program order.  Single GPU only (the
+        # peer-memory BatchNorm kernels of the data-parallel step wait on other ranks and must not be reordered).
+        self.lanes = max(1, int(lanes)) if dp is None else 1
+        self._lane_streams = []
+        self._stats = E.StatLog() if self.lanes > 1 else None
+        self._packed = E.collect_packed(model, ema_model)
         self._graphs = {}
         self._eager_steps = 0
         self._eager_by_key = {}
@@ -144,8 +153,36 @@ class SSLTrainer:
     def consistency_weight(self, iter_num):
         return self.consistency * sigmoid_rampup(iter_num // (self.max_iterations / self.consistency_rampup), self.consistency_rampup)
 
+    _SLOT = dict(t1=0, t2=1, t3=2, s0=0, lb=1, ul=2, lu=3, s=4, lq=5)      # forward order per model (train.py:643-647,668,699-702,740)
+
+    def _multi(self):
+        return self.lanes > 1 and self._eager_steps > 0 and E.PROFILE_EVENTS is None
+
+    def _run_jobs(self, jobs):
+        """Enqueue independent jobs round-robin on the lane streams (fork from / join into the current stream)."""
+        K = min(self.lanes, len(jobs)) if self._multi() else 1
+        if K <= 1:
+            return [j() for j in jobs]
+        main = torch.cuda.current_stream()
+        while len(self._lane_streams) < K:
+            self._lane_streams.append(torch.cuda.Stream())
+        ev = torch.cuda.Event()
+        ev.record(main)
+        results = []
+        for i, job in enumerate(jobs):
+            st = self._lane_streams[i % K]
+            if i < K:
+                st.wait_event(ev)
+            with torch.cuda.stream(st):
+                results.append(job())
+        for st in self._lane_streams[:K]:
+            main.wait_stream(st)
+        return results
+
     def _forward(self, model, a: E.Act, need_grad: bool, tag: str = None):
-        ctx = E.Ctx(model.training, need_grad, bn_sync=bridge.BN_SYNC)
+        multi = self._multi()
+        ctx = E.Ctx(model.training, need_grad, bn_sync=bridge.BN_SYNC, stats=self._stats if multi else None, slot=self._SLOT.get(tag, 0),
+                    grads_on_side=multi)
         ctx.bn_world = bridge.BN_WORLD
         kw = self.forward_kwargs
         if self._domains is not None:
@@ -155,25 +192,34 @@ class SSLTrainer:
 
     def _grad_provider(self, param):
         self._touched.add(id(param))
-        if self.dp is not None:
-            self.dp.on_grad_requested(param, self._last_branch)
         return self.opt.grad_for(param)
+
+    def _grad_done(self, param):
+        if self.dp is not None:
+            self.dp.on_grad_done(param, self._last_branch)
 
     def _branch(self, a, target_u8, mask_u8, weight_idx, tag):
         """forward -> loss -> backward of one loss branch; returns loss3 device tensor.  ``weight_idx``: slot of the hyper
         block holding this term's outer weight (1, cw, cw, cw^2: train.py:838)."""
         ctx, logits, head_bwd = self._forward(self.model, a, True, tag)
-        if self.dp is not None and self.dp.global_loss:
+        if self.dp is not None and self.dp.global_loss and self.dp.active:
             loss3, coef = term_forward(logits, target_u8, mask_u8, self.branch, allreduce=self.dp.sum_across_ranks, world=self.dp.world)
         else:
             loss3, coef = term_forward(logits, target_u8, mask_u8, self.branch)
         dlogits = term_backward(logits, target_u8, mask_u8, self.branch, coef, upstream=self.hyper[weight_idx:weight_idx + 1])
-        sink = E.GradSink(provider=self._grad_provider)
+        sink = E.GradSink(provider=self._grad_provider, done=self._grad_done)
         head_bwd(dlogits, sink)
-        ctx.backward(sink)
+        ctx.backward(sink, join=not self._multi())       # multi-lane: one join before the optimiser
         if self.dp is not None:
             self.dp.on_branch_done()
         return loss3, logits
+
+    def _last_branch_job(self, a, target_u8, mask_u8):
+        self._last_branch = True          # from here on finished gradient buckets may be all-reduced
+        try:
+            return self._branch(a, target_u8, mask_u8, H_CW2, "s")
+        finally:
+            self._last_branch = False
 
     def _set_hyper(self, it, gscale):
         """Write this step's scalars (host double arithmetic exactly as train.py:819-820,838,91,854) to the device block."""
@@ -287,28 +333,35 @@ class SSLTrainer:
             from .fft_mix import amp_mix
             b = dict(b)
             b["move_transx"] = amp_mix(b["cut_img"].float()[choice_i.long()], b["ulb_w"], b["mix_ratio"], self.fft_window)
-        # 1. teacher
-        _, t1, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], None, None), False, "t1")
-        _, t2, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], b["cut_img"], box_u8, choice_i), False, "t2")
-        _, t3, _ = self._forward(self.ema_model, mix_input(b["ulb_w"], b["cut_img"], inv_box, choice_i), False, "t3")
-        # 2. student on ulb_w (no grad)
-        _, s0, _ = self._forward(self.model, mix_input(b["ulb_w"], None, None), False, "s0")
+        multi = self._multi()
+        if multi:
+            self._stats.begin_step()
+            E.prepack(self._packed)                   # on this stream, before the lanes fork
+        # 1. teacher (train-mode BN, no grad) and 2. student on ulb_w (no grad): four independent forwards
+        fwd = lambda model, tag, *mix: (lambda: self._forward(model, mix_input(*mix), False, tag)[1])
+        t1, t2, t3, s0 = self._run_jobs([fwd(self.ema_model, "t1", b["ulb_w"], None, None),
+                                          fwd(self.ema_model, "t2", b["ulb_w"], b["cut_img"], box_u8, choice_i),
+                                          fwd(self.ema_model, "t3", b["ulb_w"], b["cut_img"], inv_box, choice_i),
+                                          fwd(self.model, "s0", b["ulb_w"], None, None)])
         # 3. pseudo labels
         comp = pseudo_labels(t1, t2, t3, box_u8, b["cut_label"], b["cut_mask"], choice_i, self.threshold, branch, student_logits=s0)
-        # 4. four loss branches
+        # 4. four loss branches (+ the batch-1 low-quality forward, which only feeds BatchNorm running statistics)
         self.opt.zero_grad()
         self._touched = set()
         if self.dp is not None:
             self.dp.begin_step(self.opt)
         lb_t = as_u8(b["lb_mask"]).contiguous()
-        l_sup, lg_lb = self._branch(mix_input(b["lb_x"], None, None), lb_t, None, H_ONE, "lb")
-        l_ul, lg_ul = self._branch(mix_input(b["ulb_s"], b["move_transx"], box_u8), comp["pseudo_label_ul"], comp["mask_ul"], H_CW, "ul")
-        l_lu, lg_lu = self._branch(mix_input(b["move_transx"], b["ulb_s"], box_u8), comp["pseudo_label_lu"], comp["mask_lu"], H_CW, "lu")
-        self._last_branch = True          # from here on finished gradient buckets may be all-reduced
-        l_s, lg_s = self._branch(mix_input(b["ulb_s"], None, None), comp["pseudo_label_w"], comp["mask_w"], H_CW2, "s")
-        self._last_branch = False
+        jobs = [lambda: self._branch(mix_input(b["lb_x"], None, None), lb_t, None, H_ONE, "lb"),
+                lambda: self._branch(mix_input(b["ulb_s"], b["move_transx"], box_u8), comp["pseudo_label_ul"], comp["mask_ul"], H_CW, "ul"),
+                lambda: self._branch(mix_input(b["move_transx"], b["ulb_s"], box_u8), comp["pseudo_label_lu"], comp["mask_lu"], H_CW, "lu"),
+                lambda: self._last_branch_job(mix_input(b["ulb_s"], None, None), comp["pseudo_label_w"], comp["mask_w"])]
         if lq is not None:
-            self._forward(self.model, mix_input(lq, None, None), False, "lq")
+            jobs.append(lambda: self._forward(self.model, mix_input(lq, None, None), False, "lq")[1])
+        res = self._run_jobs(jobs)
+        (l_sup, lg_lb), (l_ul, lg_ul), (l_lu, lg_lu), (l_s, lg_s) = res[:4]
+        if multi:
+            E.join_side_stream()                      # every weight / BatchNorm-parameter gradient is complete
+            self._stats.flush()                       # running statistics in the reference's forward order
         # 5. data-parallel gradient reduction (averaging folded into the optimiser's grad_scale)
         if self.dp is not None:
             self.dp.finish_step(self.opt)
