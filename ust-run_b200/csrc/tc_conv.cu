@@ -216,7 +216,7 @@ template <int BN, bool ROW> struct FwdCfg {
 // only.  Those layers were bound by re-loading the weights for every 128-pixel tile (L2->SM traffic and
 // shared-memory fill bandwidth), not by the tensor pipe.
 template <int BN, bool ROW, bool RESB>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
           const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
           const TcConvParams p) {
@@ -257,7 +257,14 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-
+  // Register budget per role (setmaxnreg): the kernel is compiled for 168 registers per thread (__launch_bounds__(384, 1);
+  // it is launched with 256 threads = 43 K registers per CTA instead of the whole 64 K file), the producer / MMA-issue /
+  // TMEM-allocator warpgroup gives back all but 56, the four epilogue warps -- 128 BatchNorm-statistics accumulators plus a
+  // 32-column TMEM slice per thread -- grow to 248.  The 22 K registers the CTA no longer holds are what lets a block of
+  // the HBM-bound BatchNorm / pooling kernels of ANOTHER lane (multi-lane step) run on the same SM next to this CTA.
+  // ptxas allocates per region only for code DOMINATED by the setmaxnreg instruction: the role code is nested under it.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     if (elect_one()) {
       if constexpr (RESB) {                    // the CTA's whole weight block, once
@@ -361,7 +368,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 248;");
     const int q = warp - 4;                     // TMEM lane quadrant
     const int row = q * 32 + lane;              // pixel row inside the tile
     const int epi_tid = threadIdx.x - 128;

@@ -334,10 +334,11 @@ class StatLog:
                 tab[i]["nbt"] = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else 0
                 tab[i]["stats"], tab[i]["C"], tab[i]["mask"] = stats.data_ptr(), bn.num_features, mask
                 tab[i]["mom"] = 0.1 if bn.momentum is None else float(bn.momentum)
-            dev = live[0][1].device
-            t = torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).to(dev)
-            ent = self._tables[key] = (t, len(live), max(e[0].num_features for e in live))
-        t, n, cmax = ent
+            host = torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).pin_memory()     # pinned + stream-ordered: legal in a capture
+            t = torch.empty(host.numel(), dtype=torch.uint8, device=live[0][1].device)
+            t.copy_(host, non_blocking=True)
+            ent = self._tables[key] = (t, len(live), max(e[0].num_features for e in live), host)
+        t, n, cmax = ent[:3]
         _call("ustrun_bn_running_update", _ptr(t), n, cmax, _stream())
 
 

@@ -42,8 +42,7 @@ class FusedSGDEMA:
         self.nblocks = len(blk_t)
         self.blk_tensor = torch.tensor(blk_t, dtype=torch.int32, device=dev)
         self.blk_offset = torch.tensor(blk_o, dtype=torch.int64, device=dev)
-        self._table_dev = torch.empty(len(self.params) * 48, dtype=torch.uint8, device=dev)
-        self._table_key = None
+        self._tables = {}
 
     # -- checkpointing: same layout as torch.optim.SGD.state_dict() (utils/util.py:259-273 saves it, train.py:544 restores it)
     def state_dict(self):
@@ -70,7 +69,7 @@ class FusedSGDEMA:
                 p = self.params[pos]
                 self.flat_buf[self.offsets[pos]: self.offsets[pos] + p.numel()].view(p.shape).copy_(st["momentum_buffer"])
                 self.first[pos] = False
-        self._table_key = None
+        self._tables = {}
 
     def grad_view(self, i):
         p = self.params[i]
@@ -86,8 +85,12 @@ class FusedSGDEMA:
         self.flat_grad.zero_()
 
     def _table(self):
+        """Device descriptor table for the current (first, has_grad) flags.  One cached table per flag set (DSBN: the set of
+        BatchNorm tensors that received gradients depends on the domains of the step), uploaded from a PINNED host copy with a
+        stream-ordered copy: legal inside a CUDA-graph capture, where it becomes a 3 KB memcpy node of the graph."""
         key = (tuple(self.first), tuple(self.has_grad), tuple(p.data_ptr() for p in self.params))
-        if key != self._table_key:
+        ent = self._tables.get(key)
+        if ent is None:
             dt = np.dtype([("p", "<u8"), ("g", "<u8"), ("buf", "<u8"), ("ema", "<u8"), ("n", "<i8"), ("first", "<i4"), ("pad", "<i4")])
             tab = np.zeros(len(self.params), dtype=dt)
             for i, p in enumerate(self.params):
@@ -98,9 +101,13 @@ class FusedSGDEMA:
                 tab[i]["ema"] = self.ema[i].data_ptr() if self.ema[i] is not None else 0
                 tab[i]["n"] = p.numel()
                 tab[i]["first"] = 1 if self.first[i] else 0
-            self._table_dev.copy_(torch.from_numpy(tab.view(np.uint8).reshape(-1)), non_blocking=False)
-            self._table_key = key
-        return self._table_dev
+            host = torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).pin_memory()
+            dev = torch.empty(host.numel(), dtype=torch.uint8, device=self.flat_grad.device)
+            dev.copy_(host, non_blocking=True)
+            if len(self._tables) > 64:
+                self._tables.clear()
+            ent = self._tables[key] = (dev, host)
+        return ent[0]
 
     def step(self, lr=None, alpha=None, grad_scale=1.0, do_sgd=True, hyper=None, do_ema=None):
         """SGD step with the gradients currently in the flat buffer, then (alpha given) EMA.

@@ -307,10 +307,10 @@ class SSLTrainer:
                 out = self._step_body(static, static_lq, keep_logits, domains)
             ent = self._graphs[key] = (g, static, static_lq, out, E.KERNELS - k0, list(self.opt.has_grad))
         g, static, static_lq, out, self.launches_per_step, has_grad = ent
-        if has_grad != self.opt.has_grad:            # another signature (DSBN domains) ran in between: restore this graph's descriptor table
-            for i, f in enumerate(has_grad):
-                self.opt.set_has_grad(i, f)
-        self.opt._table()
+        for i, f in enumerate(has_grad):             # host-side bookkeeping of the optimiser follows the graph that runs
+            self.opt.set_has_grad(i, f)
+            if f:
+                self.opt.first[i] = False
         for k, v in tensors.items():
             static[k].copy_(v, non_blocking=True)
         if lq is not None:
