@@ -179,7 +179,7 @@ struct TcConvParams {
                          // units = number of boxes (= m_tiles when halves == 1)
   float* partials;       // [ctas_per_n][2][Cout] or null
   const float* bias;     // [Cout] or null
-  int stages, nstaging;  // RESB only: depth of the activation ring / number of 16 KB store staging buffers
+  int stages, nstaging;  // depth of the TMA ring / number of 16 KB store staging buffers
   uint32_t wres_bytes;   // RESB only: bytes of the resident weight block (ntaps * Cin/64 slots of BN x 128 B)
 };
 
@@ -221,8 +221,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
           const TcConvParams p) {
   using Cfg = FwdCfg<BN, ROW>;
-  const int S = RESB ? p.stages : Cfg::stages;
-  const int nstg = RESB ? p.nstaging : Cfg::nstaging;
+  const int S = p.stages;          // ring depth and store-staging buffers: chosen on the host (launch_fwd)
+  const int nstg = p.nstaging;
   const uint32_t stage_stride = RESB ? Cfg::stageA : Cfg::stage;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_al = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -946,6 +946,18 @@ static int launch_fwd_impl(const ActView* a, int nmaps, const void* w, long long
   return check_launch("k_tc_conv");
 }
 
+// USTRUN_TC_COSHARE (default 1): leave >= 16 KB of the SM's shared memory and (setmaxnreg) 22 K registers unused by a conv CTA,
+// so that a block of an HBM-bound BatchNorm / pooling kernel running on another stream can be resident next to it.
+static int coshare_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USTRUN_TC_COSHARE");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+constexpr uint32_t kCoshareFree = 17 * 1024;
+
 template <int BN, bool ROW = false>
 static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot, const ActView& out, TcConvParams p, cudaStream_t st) {
   using Cfg = FwdCfg<BN, ROW>;
@@ -960,7 +972,7 @@ static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot
     // measured on B200 (profiles/r01_kernel_microbench_cfg2.txt): pays off for the row-mode N=128 tiles (3 x 16 KB of
     // weights per stage otherwise); for N=64 tiles the weight slots are small and the plain ring is as fast
     if ((resb_mode() > 1 || (resb_mode() == 1 && ROW && BN == 128)) && wres <= 148 * 1024 && tiles_per_cta >= 3) {
-      const long long avail = (long long)kMaxDynSmem - 2048 - wres;
+      const long long avail = (long long)kMaxDynSmem - 2048 - wres - (coshare_mode() > 0 ? kCoshareFree : 0);
       int nstg = 2;
       long long stages = (avail - nstg * 16384) / Cfg::stageA;
       if (stages < 4) { nstg = 1; stages = (avail - nstg * 16384) / Cfg::stageA; }
@@ -973,7 +985,14 @@ static int launch_fwd(const ActView* a, int nmaps, const void* w, long long Ktot
       }
     }
   }
-  return launch_fwd_impl<BN, ROW, false>(a, nmaps, w, Ktot, out, p, Cfg::smem, st);
+  p.stages = Cfg::stages; p.nstaging = Cfg::nstaging;
+  uint32_t smem_bytes = Cfg::smem;
+  if (coshare_mode() > 0 && smem_bytes + kCoshareFree > kMaxDynSmem) {
+    // BN = 256 keeps its 4 ring stages (48 KB each) and gives up one store-staging buffer; narrower tiles give up one stage
+    if (BN == 256 && p.nstaging > 1) { p.nstaging -= 1; smem_bytes -= 16384; }
+    else { p.stages -= 1; smem_bytes -= Cfg::stage; }
+  }
+  return launch_fwd_impl<BN, ROW, false>(a, nmaps, w, Ktot, out, p, smem_bytes, st);
 }
 
 // x: [B,H,W,Cin] (ldx), y: [B,H,W,Cout] (ldy); generic entry used by conv3x3/1x1 fwd+dgrad
