@@ -7,6 +7,8 @@
 
 #include <stdlib.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ustrun {
@@ -39,6 +41,27 @@ const char* last_error() { return g_err; }
     set_error("bad dtype %d", (int)(dtype));                         \
     return USTRUN_ERR_ARG;                                           \
   }
+
+// The tcgen05 conv CTAs run with the maximum shared-memory carve-out (228 KB).  A kernel launched with another carve-out
+// cannot be resident on an SM until that SM has drained, so the HBM-bound BatchNorm / pooling kernels -- whose blocks are
+// meant to run NEXT TO a conv CTA of another lane (multi-lane step) -- ask for the same configuration (they stream and do not
+// need the L1).  USTRUN_BN_CARVEOUT=0 keeps the driver's default (A/B comparisons).
+static int carveout_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USTRUN_BN_CARVEOUT");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+#define PREFER_MAX_SHARED(kernel)                                                                                   \
+  do {                                                                                                              \
+    static bool done_ = false;                                                                                      \
+    if (!done_) {                                                                                                   \
+      if (carveout_mode() > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+      done_ = true;                                                                                                 \
+    }                                                                                                               \
+  } while (0)
 
 static inline int grid_for(long long items, int threads, int cap = 148 * 16) {
   long long b = (items + threads - 1) / threads;
@@ -713,6 +736,7 @@ int ustrun_bn_finalize(const float* partials, int nparts, int C, double count, c
   USTRUN_REQUIRE(!stat_out || (training && !running_mean && !running_var && !nbt), "bn_finalize: stat_out replaces the in-place running update");
   USTRUN_REQUIRE(!training || (partials && nparts > 0 && count > 0), "bn_finalize: training needs partials");
   USTRUN_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval needs running stats");
+  PREFER_MAX_SHARED(k_bn_finalize);
   k_bn_finalize<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, beta, conv_bias, running_mean,
                                                                    running_var, nbt, momentum, eps, training, scale, shift, mean, rstd, stat_out);
   return check_launch("bn_finalize");
@@ -730,13 +754,13 @@ int ustrun_bn_act_fwd(const void* x, int ldx, const float* scale, const float* s
   if (pooled) {
     USTRUN_REQUIRE(H % 2 == 0 && W % 2 == 0 && ldp % 8 == 0, "bn_act_fwd: pooling needs even H, W");
     long long n = npix / 4 * (C / 8);
-    DISPATCH_DTYPE(dtype, (k_bn_act_pool<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, scale, shift, act, (T*)y,
+    DISPATCH_DTYPE(dtype, (PREFER_MAX_SHARED(k_bn_act_pool<T>), k_bn_act_pool<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, scale, shift, act, (T*)y,
                                                                                                ldy, (T*)pooled, ldp, B, H, W, C)));
   } else {
     long long n = npix * (C / 8);
     int grid = grid_for(n, 256);
     while (((long long)grid * 256) % (C / 8)) ++grid;          // a thread must keep its channel group
-    DISPATCH_DTYPE(dtype, (k_bn_act<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, scale, shift, act, (T*)y, ldy, npix, C)));
+    DISPATCH_DTYPE(dtype, (PREFER_MAX_SHARED(k_bn_act<T>), k_bn_act<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, scale, shift, act, (T*)y, ldy, npix, C)));
   }
   return check_launch("bn_act_fwd");
 }
@@ -753,13 +777,14 @@ int ustrun_bn_bwd_reduce(const void* g, int ldg, const void* x, int ldx, const f
   if (!waves) { const char* e = getenv("USTRUN_BN_BWD_WAVES"); waves = e ? atoi(e) : 1; if (waves < 1) waves = 1; }
   if (grid > 148 * 3 * waves) grid = 148 * 3 * waves;
   *nparts_host = grid;
-  DISPATCH_DTYPE(dtype, (k_bn_bwd_reduce<T><<<grid, 256, 256 * 8 * sizeof(float), (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, (PREFER_MAX_SHARED(k_bn_bwd_reduce<T>), k_bn_bwd_reduce<T><<<grid, 256, 256 * 8 * sizeof(float), (cudaStream_t)stream>>>(
                             (const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale, shift, act, npix, C, partials)));
   return check_launch("bn_bwd_reduce");
 }
 int ustrun_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* rstd, float* dgamma,
                            float* dbeta, int accumulate, float param_grad_scale, float* coef, void* stream) {
   USTRUN_REQUIRE(partials && nparts > 0 && C > 0 && rstd && count > 0 && (coef || dgamma || dbeta), "bn_bwd_finalize: bad args");
+  PREFER_MAX_SHARED(k_bn_bwd_finalize);
   k_bn_bwd_finalize<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, count, gamma, rstd, dgamma, dbeta, accumulate, param_grad_scale, coef);
   return check_launch("bn_bwd_finalize");
 }
@@ -769,7 +794,7 @@ int ustrun_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, const fl
   long long n = npix * (C / 8);
   int grid = grid_for(n, 256);
   while (((long long)grid * 256) % (C / 8)) ++grid;            // a thread must keep its channel group
-  DISPATCH_DTYPE(dtype, (k_bn_bwd_apply<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale,
+  DISPATCH_DTYPE(dtype, (PREFER_MAX_SHARED(k_bn_bwd_apply<T>), k_bn_bwd_apply<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)g, ldg, (const T*)x, ldx, mean, rstd, scale,
                                                                                   shift, coef, act, (T*)dx, lddx, npix, C)));
   return check_launch("bn_bwd_apply");
 }
@@ -778,7 +803,7 @@ int ustrun_maxpool_bwd(const void* y, int ldy, const void* dpool, int ldp, const
   USTRUN_REQUIRE(y && dpool && gout && C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && ldy % 8 == 0 && ldp % 8 == 0 && ldgo % 8 == 0 &&
                      (!gskip || ldgs % 8 == 0), "maxpool_bwd: bad args");
   long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
-  DISPATCH_DTYPE(dtype, (k_maxpool_bwd<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y, ldy, (const T*)dpool, ldp, (const T*)gskip,
+  DISPATCH_DTYPE(dtype, (PREFER_MAX_SHARED(k_maxpool_bwd<T>), k_maxpool_bwd<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y, ldy, (const T*)dpool, ldp, (const T*)gskip,
                                                                                              ldgs, (T*)gout, ldgo, B, H, W, C)));
   return check_launch("maxpool_bwd");
 }
