@@ -45,12 +45,14 @@ const char* last_error() { return g_err; }
 // The tcgen05 conv CTAs run with the maximum shared-memory carve-out (228 KB).  A kernel launched with another carve-out
 // cannot be resident on an SM until that SM has drained, so the HBM-bound BatchNorm / pooling kernels -- whose blocks are
 // meant to run NEXT TO a conv CTA of another lane (multi-lane step) -- ask for the same configuration (they stream and do not
-// need the L1).  USTRUN_BN_CARVEOUT=0 keeps the driver's default (A/B comparisons).
+// need the L1).  Measured on B200 (tools/coreside_probe.py, profiles/r02_coreside_probe.txt): OFF by default -- with the hint
+// the streaming kernels themselves slow down (bn_act 52 -> 59 us, bn_bwd_apply 77 -> 101 us for 151 MB) and the conv + BN
+// pair still takes ~0.85 x the sum of the two, i.e. the blocks do not run side by side.  USTRUN_BN_CARVEOUT=1 enables it.
 static int carveout_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("USTRUN_BN_CARVEOUT");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 0;
   }
   return v;
 }

@@ -946,13 +946,15 @@ static int launch_fwd_impl(const ActView* a, int nmaps, const void* w, long long
   return check_launch("k_tc_conv");
 }
 
-// USTRUN_TC_COSHARE (default 1): leave >= 16 KB of the SM's shared memory and (setmaxnreg) 22 K registers unused by a conv CTA,
-// so that a block of an HBM-bound BatchNorm / pooling kernel running on another stream can be resident next to it.
+// USTRUN_TC_COSHARE=1: leave >= 16 KB of the SM's shared memory (and, always, via setmaxnreg 22 K registers) unused by a conv
+// CTA, so that a block of an HBM-bound BatchNorm / pooling kernel running on another stream could be resident next to it.
+// Measured (tools/coreside_probe.py): no co-residency gain on B200 -- conv + BN launched on two streams take ~0.85 x the sum
+// of the two either way (tail overlap only) -- and the shallower ring costs the conv ~2 %, so it is OFF by default.
 static int coshare_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("USTRUN_TC_COSHARE");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 0;
   }
   return v;
 }
