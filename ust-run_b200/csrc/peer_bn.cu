@@ -3,63 +3,81 @@
 // Data-parallel BN needs, per layer and pass, the sum over ranks of a tiny [2*C] vector
 // (forward: sum x, sum x^2; backward: sum g', sum g' xhat).  As separate launches that is a partial-row
 // reduction kernel + an NCCL all-reduce (latency ~20-50 us, 230+ times per step) + the finalize
-// kernel.  Here ONE kernel does all three: every warp reduces its channel's partial rows, publishes
-// the two doubles in this rank's symmetric buffer, the last warp of the grid pushes a sequence flag into
-// every peer's flag array (st over NVLink), all warps wait for the peers' flags in LOCAL memory, read
-// the peers' doubles with peer loads and finish the BatchNorm maths -- identical summation order on
-// every rank, so all ranks compute bit-identical statistics.
+// kernel.  Here ONE kernel does all three: every warp reduces its channel's partial rows and PUSHES the
+// two doubles into every rank's symmetric buffer as self-validating 8-byte packets {32 data bits, 32-bit
+// sequence number} (the "LL" protocol of collective libraries: an aligned 8-byte store is single-copy atomic,
+// so a packet whose flag equals this call's sequence number carries this call's data -- no fences, no flag
+// array, no counters).  Each warp then polls the packets the other ranks pushed into ITS OWN buffer (local
+// memory, L2 hits) and adds them in rank order: identical summation order on every rank, so all ranks compute
+// bit-identical statistics.  Cost per barrier = one NVLink store latency, instead of (round 1) a system fence,
+// a grid-wide counter, a flag store per peer and `world` dependent peer LOADS (~2 us each).
 //
 // Buffers come from torch.distributed._symmetric_memory (one allocation per rank, peer-mapped).
-// Layout of each rank's buffer: uint32 flags[32] | double data[2 slots][2][PEER_CMAX].
+// Layout of each rank's buffer: uint2 packet[2 slots][PEER_MAXW source ranks][PEER_CMAX channels][4 parts]
+// (parts: low/high word of the first double, low/high word of the second).  Two slots (sequence parity) are
+// enough: a rank can run at most one barrier ahead of any peer, because finishing barrier k needs every
+// peer's packets of barrier k, which a peer pushes only after it has finished reading barrier k-1.
 #include "common.cuh"
 
 namespace ustrun {
 
 constexpr int PEER_CMAX = 1024;
 constexpr int PEER_MAXW = 8;
-constexpr long long PEER_TIMEOUT_CYCLES = 6000000000LL;     // ~3 s: never hang the GPU on a lost peer
+constexpr long long PEER_TIMEOUT_CYCLES = 20000000000LL;    // ~10 s: never hang the GPU on a lost peer (the host polls `error`)
 
 struct PeerCtx {
   unsigned char* base[PEER_MAXW];   // peer-mapped base address of every rank's buffer (own included)
   int rank, world;
-  unsigned int seq;                 // same value on every rank for this call
-  unsigned int* counter;            // local: warps that published
+  unsigned int seq;                 // same non-zero value on every rank for this call
+  unsigned int* counter;            // unused (kept in the ABI)
   int* error;                       // local: set to 1 on timeout
 };
 
-__device__ __forceinline__ volatile unsigned int* peer_flags(const PeerCtx& p, int r) { return reinterpret_cast<volatile unsigned int*>(p.base[r]); }
-__device__ __forceinline__ double* peer_data(const PeerCtx& p, int r, int slot) {
-  return reinterpret_cast<double*>(p.base[r] + 128) + (size_t)slot * 2 * PEER_CMAX;
+__device__ __forceinline__ uint2* peer_packet(const PeerCtx& p, int dst_rank, int slot, int src_rank, int c) {
+  return reinterpret_cast<uint2*>(p.base[dst_rank]) + (((size_t)slot * PEER_MAXW + src_rank) * PEER_CMAX + c) * 4;
+}
+__device__ __forceinline__ void st_packet(uint2* dst, unsigned int data, unsigned int flag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(data), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_packet(const uint2* src) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(src) : "memory");
+  return v;
 }
 
-// lane 0 of every warp calls this with its channel's local sums; returns the sums over all ranks
-__device__ __forceinline__ void peer_allreduce2(const PeerCtx& p, int c, int nwarps, double& a, double& b) {
-  const int slot = p.seq & 1;
-  double* mine = peer_data(p, p.rank, slot);
-  mine[c] = a;
-  mine[PEER_CMAX + c] = b;
-  __threadfence_system();
-  const unsigned int prev = atomicAdd(p.counter, 1u);
-  if (prev == (unsigned int)nwarps - 1u) {                 // last publisher of this rank: signal every peer
-    *p.counter = 0u;
-    __threadfence_system();
-    for (int r = 0; r < p.world; ++r) peer_flags(p, r)[p.rank] = p.seq;
-    __threadfence_system();
+// Called by ALL 32 lanes of the warp that owns channel c, every lane holding the warp totals (a, b).  Lane l serves
+// rank l / 4, part l % 4: world <= 8 ranks x 4 packets = one packet per lane each way.  Returns the sums over all ranks
+// (in every lane); on a timeout sets *error and leaves the local sums.
+__device__ __forceinline__ void peer_allreduce2(const PeerCtx& p, int c, int lane, double& a, double& b) {
+  const unsigned int seq = p.seq;
+  const int slot = (int)(seq & 1u);
+  const int r = lane >> 2, part = lane & 3;
+  const bool active = r < p.world;
+  if (active) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(part < 2 ? a : b);
+    st_packet(peer_packet(p, r, slot, p.rank, c) + part, (part & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits, seq);
   }
-  const long long t0 = clock64();
-  volatile unsigned int* myflags = peer_flags(p, p.rank);
-  for (int r = 0; r < p.world; ++r) {
-    // flags only grow; wrap-around safe comparison
-    while ((int)(myflags[r] - p.seq) < 0) {
-      if (clock64() - t0 > PEER_TIMEOUT_CYCLES) { *p.error = 1; return; }
+  unsigned int word = 0u;
+  bool ok = true;
+  if (active) {
+    const uint2* src = peer_packet(p, p.rank, slot, r, c) + part;
+    const long long t0 = clock64();
+    for (;;) {
+      const uint2 v = ld_packet(src);
+      if (v.y == seq) { word = v.x; break; }
+      if (clock64() - t0 > PEER_TIMEOUT_CYCLES) { ok = false; break; }
     }
   }
-  __threadfence_system();
+  if (!__all_sync(0xffffffffu, ok)) {
+    if (lane == 0) *p.error = 1;
+    return;
+  }
   double sa = 0.0, sb = 0.0;
-  for (int r = 0; r < p.world; ++r) {
-    const volatile double* d = peer_data(p, r, slot);
-    sa += d[c];
-    sb += d[PEER_CMAX + c];
+  for (int rr = 0; rr < p.world; ++rr) {
+    const unsigned int a_lo = __shfl_sync(0xffffffffu, word, rr * 4 + 0), a_hi = __shfl_sync(0xffffffffu, word, rr * 4 + 1);
+    const unsigned int b_lo = __shfl_sync(0xffffffffu, word, rr * 4 + 2), b_hi = __shfl_sync(0xffffffffu, word, rr * 4 + 3);
+    sa += __longlong_as_double((long long)(((unsigned long long)a_hi << 32) | a_lo));
+    sb += __longlong_as_double((long long)(((unsigned long long)b_hi << 32) | b_lo));
   }
   a = sa;
   b = sb;
@@ -82,8 +100,8 @@ __global__ void k_bn_finalize_peer(const float* __restrict__ partials, int npart
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
+  peer_allreduce2(p, c, lane, s, q);
   if (lane != 0) return;
-  peer_allreduce2(p, c, C, s, q);
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f, cb = conv_bias ? conv_bias[c] : 0.f;
   const double m = s / count_global;
   double var = q / count_global - m * m;
@@ -126,11 +144,13 @@ __global__ void k_bn_bwd_finalize_peer(const float* __restrict__ partials, int n
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   }
-  if (lane != 0) return;
   // parameter gradients stay LOCAL sums: the gradient all-reduce adds them across ranks exactly once
-  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
-  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
-  peer_allreduce2(p, c, C, s1, s2);
+  if (lane == 0) {
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
+  }
+  peer_allreduce2(p, c, lane, s1, s2);
+  if (lane != 0) return;
   const float g = gamma ? gamma[c] : 1.f;
   coef[c] = g * rstd[c];
   coef[C + c] = (float)(s1 / count_global);
@@ -138,7 +158,7 @@ __global__ void k_bn_bwd_finalize_peer(const float* __restrict__ partials, int n
 }
 
 static int fill_ctx(PeerCtx& p, const void* const* peer_bases, int rank, int world, unsigned int seq, unsigned int* counter, int* error) {
-  if (!peer_bases || world < 1 || world > PEER_MAXW || rank < 0 || rank >= world || !counter || !error) {
+  if (!peer_bases || world < 1 || world > PEER_MAXW || rank < 0 || rank >= world || !error || seq == 0u) {
     set_error("peer BN: bad peer arguments (world %d, rank %d)", world, rank);
     return USTRUN_ERR_ARG;
   }
@@ -153,7 +173,7 @@ using namespace ustrun;
 
 extern "C" {
 
-long long ustrun_peer_buffer_bytes(void) { return 128 + 2LL * 2 * PEER_CMAX * (long long)sizeof(double); }
+long long ustrun_peer_buffer_bytes(void) { return 2LL * PEER_MAXW * PEER_CMAX * 4 * (long long)sizeof(uint2); }
 
 int ustrun_bn_finalize_peer(const float* partials, int nparts, int C, double count_global, const float* gamma, const float* beta,
                             const float* conv_bias, float* running_mean, float* running_var, long long* nbt, float momentum, float eps,

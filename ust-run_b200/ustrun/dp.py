@@ -120,9 +120,9 @@ class PeerStats:
     def args(self):
         """(peer_bases, rank, world, seq, counter, error) for ustrun_bn_*_finalize_peer; every rank
         issues the same sequence of calls, so the sequence numbers agree."""
-        self.seq += 1
+        self.seq = self.seq % 0x7FFFFFFE + 1          # 1 .. 2^31-1: never 0 (the buffers start zeroed)
         c = self._ctypes
-        return (self._bases, self.rank, self.world, self.seq & 0x7FFFFFFF, c.c_void_p(self.counter.data_ptr()), c.c_void_p(self.error.data_ptr()))
+        return (self._bases, self.rank, self.world, self.seq, c.c_void_p(self.counter.data_ptr()), c.c_void_p(self.error.data_ptr()))
 
     def check(self):
         if int(self.error.item()) != 0:
