@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--lanes", type=int, default=1)
+    ap.add_argument("--manifest", default="", help="write the profiled C-ABI calls of the LAST step (class, algorithmic work, shape) as JSON")
     a = ap.parse_args()
     model_name, c, k, H, W, Bl, Bu, branch = B.WORKLOADS[a.workload]
     E.set_precision(a.precision)
@@ -43,9 +44,16 @@ def main():
     lq = dev["ulb_w"][:1].contiguous()
     E.reserve_pool(fraction=0.3)
     for i in range(a.steps):
+        if a.manifest and i == a.steps - 1:
+            E.MANIFEST = []
         out = tr.step({**dev, **extra}, lq=lq)
         torch.cuda.synchronize()
         print(f"step {i}: loss {float(out['loss']):.5f} kernels/step {tr.launches_per_step} (total so far {E.KERNELS})", flush=True)
+
+
+    if a.manifest:
+        import json
+        json.dump({"workload": a.workload, "kernels_per_step": tr.launches_per_step, "calls": E.MANIFEST}, open(a.manifest, "w"))
 
 
 if __name__ == "__main__":

@@ -29,6 +29,7 @@ _FORCE_SIMT = os.environ.get("USTRUN_FORCE_SIMT", "0") == "1"
 LAUNCHES = 0          # C-ABI calls issued
 KERNELS = 0           # kernels those calls launched (bench.py reports it as gpu_launches)
 PROFILE_EVENTS = None  # bench.py sets this to a list: (kernel class, algorithmic FLOPs, start event, end event)
+MANIFEST = None        # tools/step_once.py sets this to a list: one dict per profiled C-ABI call, in launch order (for ncu summaries)
 _KERNELS_PER_CALL = {"ustrun_conv_wgrad": 2, "ustrun_convT2x2_wgrad": 2, "ustrun_convT2x2_fwd": 4, "ustrun_channel_sum": 2,
                      "ustrun_ce_dice_softmax_fwd": 2, "ustrun_bce_dice_sigmoid_fwd": 2}
 
@@ -96,8 +97,11 @@ def _call(name, *args):
     L.call(name, *args)
 
 
-def _profiled(cls, flops, name, *args):
-    """_call bracketed by CUDA events on the launching stream when bench.py profiles."""
+def _profiled(cls, flops, name, *args, meta=None):
+    """_call bracketed by CUDA events on the launching stream when bench.py profiles.  ``flops``: algorithmic FLOPs (tensor
+    classes) or algorithmic bytes (``hbm_*`` classes) of the call."""
+    if MANIFEST is not None:
+        MANIFEST.append({"cls": cls, "entry": name, "work": float(flops), "kernels": _KERNELS_PER_CALL.get(name, 1), "meta": meta})
     if PROFILE_EVENTS is None:
         return _call(name, *args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -446,7 +450,7 @@ def _raw_conv(x: Act, wpk, bias, y: Act, ks, partials=None, out_nchw=None):
     cout = out_nchw.shape[1] if out_nchw is not None else y.C
     _profiled("tc_conv" if impl == L.TCGEN05 else "simt_conv", 2.0 * x.npix * x.C * cout * ks * ks, "ustrun_conv_fwd", impl, x.ptr, x.ld, _ptr(wpk), _ptr(bias), _ptr(out_nchw) if out_nchw is not None else y.ptr,
           0 if out_nchw is not None else y.ld, x.dtype_code, x.B, x.H, x.W, x.C, cout, ks, 1 if out_nchw is not None else 0,
-          _ptr(partials), ctypes.byref(nparts), _stream())
+          _ptr(partials), ctypes.byref(nparts), _stream(), meta=(x.B, x.H, x.W, x.C, cout, ks))
     return nparts.value
 
 
@@ -456,7 +460,7 @@ def _wgrad(dy: Act, x: Act, dw: torch.Tensor, accumulate: int, ks: int):
     ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.t.device)
     _profiled("tc_wgrad" if impl == L.TCGEN05 else "simt_wgrad", 2.0 * x.npix * x.C * dy.C * ks * ks,
               "ustrun_conv_wgrad", impl, dy.ptr, dy.ld, x.ptr, x.ld, _ptr(dw), accumulate, x.dtype_code, x.B, x.H, x.W, x.C, dy.C, ks,
-          _ptr(ws), int(nbytes), _stream())
+          _ptr(ws), int(nbytes), _stream(), meta=(x.B, x.H, x.W, x.C, dy.C, ks))
 
 
 class BNState:
@@ -600,7 +604,10 @@ def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
     wf, wd = packed.get(up.weight, transposed=True, need_wd=ctx.need_grad or up.weight.requires_grad)
     cin, cout = up.in_channels, up.out_channels
     impl = _impl_for(cin, cout, x.dtype_code)
-    _call("ustrun_convT2x2_fwd", impl, x.ptr, x.ld, _ptr(wf), _ptr(up.bias), out.ptr, out.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream())
+    tcls = "tc_conv" if impl == L.TCGEN05 else "simt_conv"
+    tflops = 2.0 * x.npix * cin * cout * 4
+    _profiled(tcls, tflops, "ustrun_convT2x2_fwd", impl, x.ptr, x.ld, _ptr(wf), _ptr(up.bias), out.ptr, out.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream(),
+              meta=(x.B, x.H, x.W, cin, cout, "T"))
     if ctx.need_grad:
         dev = x.t.device
         gos = ctx.grads_on_side and ctx.bn_sync is None
@@ -613,8 +620,8 @@ def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
                 dw, acc = sink.get(up.weight)
                 nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(impl, x.B, x.H, x.W, cin, cout, 2)
                 ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
-                _call("ustrun_convT2x2_wgrad", impl, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code, x.B, x.H, x.W, cin, cout,
-                      _ptr(ws), int(nbytes), _stream())
+                _profiled("tc_wgrad" if impl == L.TCGEN05 else "simt_wgrad", tflops, "ustrun_convT2x2_wgrad", impl, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code,
+                          x.B, x.H, x.W, cin, cout, _ptr(ws), int(nbytes), _stream(), meta=(x.B, x.H, x.W, cin, cout, "T"))
                 sink.done(up.weight)
             on_side_stream(wgrad_fn, (G.t, x.t))
             if up.bias is not None:
@@ -629,7 +636,8 @@ def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
                     bias_fn()
             if x.needs_grad:
                 gx = Act.new(x.B, x.H, x.W, x.C, dtype=x.t.dtype, device=dev)
-                _call("ustrun_convT2x2_dgrad", impl, G.ptr, G.ld, _ptr(wd), gx.ptr, gx.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream())
+                _profiled(tcls, tflops, "ustrun_convT2x2_dgrad", impl, G.ptr, G.ld, _ptr(wd), gx.ptr, gx.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream(),
+                          meta=(x.B, x.H, x.W, cin, cout, "Td"))
                 _assign_grad(x, gx)
 
         ctx.tape.append(bwd)
