@@ -46,6 +46,19 @@ int ustrun_pack_conv_weight(const float* w, void* wf, void* wd, int dtype, int C
 /* nn.ConvTranspose2d(k2,s2) weight [Cin][Cout][2][2] -> wf[4][Cout][Cin], wd[Cin][4][Cout] */
 int ustrun_pack_convT_weight(const float* w, void* wf, void* wd, int dtype, int Cin, int Cout, void* stream);
 
+/* Every conv / transposed-conv weight of a model in ONE launch (after the optimiser step all packed copies are stale).
+ * Entry: OIHW (transposed = 0: wf[Cout][taps][Cin], wd[Cin][taps flipped][Cout]) or ConvTranspose2d [Cin][Cout][2][2]
+ * (transposed = 1: wf[4][Cout][Cin], wd[Cin][4][Cout]); wf / wd nullable.  Block i handles tile blk_tile[i] of entry
+ * blk_entry[i]: conv tiles are 32 x 32 (co, ci) numbered co_tile * ceil(Cin / 32) + ci_tile, transposed-conv tiles are runs of
+ * 4096 elements. */
+typedef struct {
+  const float* w;
+  void* wf;
+  void* wd;
+  int Cout, Cin, taps, transposed;
+} ustrun_pack_t;
+int ustrun_pack_weights_multi(const ustrun_pack_t* table, const int* blk_entry, const int* blk_tile, int nblocks, int dtype, void* stream);
+
 /* ---- convolutions (K1,K2,K3,K8,K10) ------------------------------------------------------- */
 /* nn.Conv2d 3x3 s1 p1 / 1x1 forward: unet_parts.py:16,19,74; unet.py:37-43,81,85,88,182.
  * Also used for dgrad with the `wd` packing (autograd of the same call sites).

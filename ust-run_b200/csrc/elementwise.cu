@@ -148,6 +148,49 @@ k_pack_conv(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd,
       wd[((size_t)(ci0 + ci) * taps + (taps - 1 - t)) * Cout + co0 + co] = from_f<T>(tile[co * row + ci * taps + t]);
     }
 }
+// Multi-tensor packing: ONE launch re-packs every conv / transposed-conv weight of a model after the optimiser step (46
+// launches per step for UNet-A + teacher, ~200 for UNet-B, each a few microseconds of work behind a launch).  Block i works
+// on tile blk_tile[i] of table entry blk_entry[i]: conv entries use the 32 x 32 x taps shared-memory tile of k_pack_conv,
+// transposed-conv entries a 4096-element run of the flat weight.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pack_multi(const ustrun_pack_t* __restrict__ table, const int* __restrict__ blk_entry, const int* __restrict__ blk_tile) {
+  extern __shared__ float tile[];
+  const ustrun_pack_t e = table[blk_entry[blockIdx.x]];
+  const int tl = blk_tile[blockIdx.x];
+  T* wf = (T*)e.wf;
+  T* wd = (T*)e.wd;
+  if (e.transposed) {
+    const long long n = (long long)e.Cin * e.Cout * 4, i0 = (long long)tl * 4096;
+    for (long long i = i0 + threadIdx.x; i < n && i < i0 + 4096; i += 256) {
+      const int ij = (int)(i % 4), co = (int)((i / 4) % e.Cout), ci = (int)(i / (4LL * e.Cout));
+      const float v = e.w[i];
+      if (wf) wf[((size_t)ij * e.Cout + co) * e.Cin + ci] = from_f<T>(v);
+      if (wd) wd[((size_t)ci * 4 + ij) * e.Cout + co] = from_f<T>(v);
+    }
+    return;
+  }
+  const int Cout = e.Cout, Cin = e.Cin, taps = e.taps;
+  const int ci_tiles = (Cin + 31) >> 5;
+  const int co0 = (tl / ci_tiles) * 32, ci0 = (tl % ci_tiles) * 32;
+  const int nco = min(32, Cout - co0), nci = min(32, Cin - ci0);
+  const int row = 32 * taps + 1;
+  for (int i = threadIdx.x; i < nco * nci * taps; i += 256) {
+    const int co = i / (nci * taps), r = i - co * (nci * taps);
+    tile[co * row + r] = e.w[((size_t)(co0 + co) * Cin + ci0) * taps + r];
+  }
+  __syncthreads();
+  if (wf)
+    for (int i = threadIdx.x; i < nco * taps * nci; i += 256) {
+      const int ci = i % nci, t = (i / nci) % taps, co = i / (nci * taps);
+      wf[((size_t)(co0 + co) * taps + t) * Cin + ci0 + ci] = from_f<T>(tile[co * row + ci * taps + t]);
+    }
+  if (wd)
+    for (int i = threadIdx.x; i < nci * taps * nco; i += 256) {
+      const int co = i % nco, t = (i / nco) % taps, ci = i / (nco * taps);
+      wd[((size_t)(ci0 + ci) * taps + (taps - 1 - t)) * Cout + co0 + co] = from_f<T>(tile[co * row + ci * taps + t]);
+    }
+}
 // ConvTranspose2d weight [Cin][Cout][2][2]
 template <typename T>
 __global__ void k_pack_convT(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cin, int Cout) {
@@ -720,6 +763,12 @@ int ustrun_pack_conv_weight(const float* w, void* wf, void* wd, int dtype, int C
   const size_t smem = (size_t)32 * (32 * taps + 1) * sizeof(float);
   DISPATCH_DTYPE(dtype, (k_pack_conv<T><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (T*)wf, (T*)wd, Cout, Cin, taps)));
   return check_launch("pack_conv_weight");
+}
+int ustrun_pack_weights_multi(const ustrun_pack_t* table, const int* blk_entry, const int* blk_tile, int nblocks, int dtype, void* stream) {
+  USTRUN_REQUIRE(table && blk_entry && blk_tile && nblocks > 0, "pack_weights_multi: bad args");
+  const size_t smem = (size_t)32 * (32 * 9 + 1) * sizeof(float);
+  DISPATCH_DTYPE(dtype, (k_pack_multi<T><<<nblocks, 256, smem, (cudaStream_t)stream>>>(table, blk_entry, blk_tile)));
+  return check_launch("pack_weights_multi");
 }
 int ustrun_pack_convT_weight(const float* w, void* wf, void* wd, int dtype, int Cin, int Cout, void* stream) {
   USTRUN_REQUIRE(w && (wf || wd) && Cout > 0 && Cin > 0, "pack_convT_weight: bad args");

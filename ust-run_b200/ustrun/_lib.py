@@ -39,6 +39,7 @@ _SIGS = {
     "ustrun_nhwc_to_nchw": [p, i32, i32, p, i32, i32, i32, i32, p],
     "ustrun_pack_conv_weight": [p, p, p, i32, i32, i32, i32, p],
     "ustrun_pack_convT_weight": [p, p, p, i32, i32, i32, p],
+    "ustrun_pack_weights_multi": [p, p, p, i32, i32, p],
     "ustrun_conv_fwd": [i32, p, i32, p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, p, ip, p],
     "ustrun_conv_wgrad": [i32, p, i32, p, i32, p, i32, i32, i32, i32, i32, i32, i32, i32, p, i64, p],
     "ustrun_convT2x2_fwd": [i32, p, i32, p, p, p, i32, i32, i32, i32, i32, i32, i32, p],

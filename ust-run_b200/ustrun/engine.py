@@ -357,6 +357,69 @@ def collect_packed(*models):
     return [p for p in out if isinstance(p, PackedConv)]
 
 
+class PackPlan:
+    """All packed weight copies of a set of convs refreshed by ONE launch (ustrun_pack_weights_multi) on the current stream:
+    after the optimiser step every copy of the student and of the teacher is stale, and packing them lazily is 46 (UNet-A) to
+    ~200 (UNet-B) few-microsecond launches per step.  Only convs that have run before are known (``PackedConv.last``); the
+    others keep packing lazily on first use."""
+
+    def __init__(self, packed_list):
+        self.packed = packed_list
+        self._sig = None
+        self._dev = None
+
+    @staticmethod
+    def _key(weight, code):
+        return (weight.data_ptr(), weight._version, code, getattr(weight, "_ustrun_epoch", 0))
+
+    def run(self):
+        import numpy as np
+        tdt, code = _dt()
+        ents = []
+        for pk in self.packed:
+            if pk.last is None:
+                continue
+            w = pk.last[0]()
+            if w is None or not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous():
+                continue
+            ents.append((pk, w, pk.last[1], pk.last[2]))
+        if not ents or all(pk.key == self._key(w, code) and (pk.has_wd or not nwd) for pk, w, _, nwd in ents):
+            return
+        sig = tuple((id(pk), w.data_ptr(), code, tr, nwd) for pk, w, tr, nwd in ents)
+        if sig != self._sig:
+            dt = np.dtype([("w", "<u8"), ("wf", "<u8"), ("wd", "<u8"), ("Cout", "<i4"), ("Cin", "<i4"), ("taps", "<i4"), ("tr", "<i4")])
+            tab = np.zeros(len(ents), dtype=dt)
+            be, bt = [], []
+            for i, (pk, w, tr, nwd) in enumerate(ents):
+                if tr:
+                    cin, cout, taps = w.shape[0], w.shape[1], 4
+                    fshape, dshape = (4, cout, cin), (cin, 4, cout)
+                    ntiles = (cin * cout * 4 + 4095) // 4096
+                else:
+                    cout, cin, taps = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+                    fshape, dshape = (cout, taps, cin), (cin, taps, cout)
+                    ntiles = ((cout + 31) // 32) * ((cin + 31) // 32)
+                if pk.wf is None or pk.wf.dtype != tdt or tuple(pk.wf.shape) != fshape:
+                    pk.wf = torch.empty(fshape, dtype=tdt, device=w.device)
+                if nwd and (pk.wd is None or pk.wd.dtype != tdt or tuple(pk.wd.shape) != dshape):
+                    pk.wd = torch.empty(dshape, dtype=tdt, device=w.device)
+                tab[i] = (w.data_ptr(), pk.wf.data_ptr(), pk.wd.data_ptr() if nwd else 0, cout, cin, taps, 1 if tr else 0)
+                be += [i] * ntiles
+                bt += list(range(ntiles))
+            dev = ents[0][1].device
+            up = lambda a: torch.from_numpy(a).pin_memory()
+            host = (up(tab.view(np.uint8).reshape(-1).copy()), up(np.asarray(be, np.int32)), up(np.asarray(bt, np.int32)))
+            self._dev = tuple(torch.empty_like(h, device=dev) for h in host) + (len(be), host)
+            for d, h in zip(self._dev[:3], host):
+                d.copy_(h, non_blocking=True)
+            self._sig = sig
+        t, e, b, n, _ = self._dev
+        _call("ustrun_pack_weights_multi", _ptr(t), _ptr(e), _ptr(b), n, code, _stream())
+        for pk, w, _, nwd in ents:
+            pk.key = self._key(w, code)
+            pk.has_wd = bool(nwd)
+
+
 def prepack(packed_list):
     """Refresh the packed weight copies on the CURRENT stream (multi-lane step: before the lanes fork, so that no lane
     depends on a packing kernel another lane launched).  Only convs that have run before are known."""

@@ -142,7 +142,7 @@ class SSLTrainer:
         self.lanes = max(1, int(lanes)) if dp is None else 1
         self._lane_streams = []
         self._stats = E.StatLog() if self.lanes > 1 else None
-        self._packed = E.collect_packed(model, ema_model)
+        self._pack_plan = E.PackPlan(E.collect_packed(model, ema_model))
         self._graphs = {}
         self._eager_steps = 0
         self._eager_by_key = {}
@@ -334,9 +334,10 @@ class SSLTrainer:
             b = dict(b)
             b["move_transx"] = amp_mix(b["cut_img"].float()[choice_i.long()], b["ulb_w"], b["mix_ratio"], self.fft_window)
         multi = self._multi()
+        if self._eager_steps > 0:
+            self._pack_plan.run()                     # every packed weight copy in one launch, on this stream, before the lanes fork
         if multi:
             self._stats.begin_step()
-            E.prepack(self._packed)                   # on this stream, before the lanes fork
         # 1. teacher (train-mode BN, no grad) and 2. student on ulb_w (no grad): four independent forwards
         fwd = lambda model, tag, *mix: (lambda: self._forward(model, mix_input(*mix), False, tag)[1])
         t1, t2, t3, s0 = self._run_jobs([fwd(self.ema_model, "t1", b["ulb_w"], None, None),
