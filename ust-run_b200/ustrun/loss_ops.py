@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from . import _lib as L
-from .engine import _call, _ptr, _stream
+from .engine import _call, _profiled, _ptr, _stream
 
 
 def as_u8(t: torch.Tensor) -> torch.Tensor:
@@ -48,15 +48,18 @@ def term_forward(logits, target_u8, mask_u8, branch, ce_w=1.0, dice_w=1.0, class
             allreduce(sums)
             _call("ustrun_bce_dice_sigmoid_finalize", _ptr(sums), 1, float(B * C * H * W) * world, float(ce_w), float(dice_w), _ptr(coef), _ptr(loss3), _stream())
         return loss3, coef
+    # algorithmic bytes of pass 1: the logits once (fp32) + target / mask bytes
+    nlab = B * H * W * (1 if branch == "softmax" else C)
+    p1_bytes = B * C * H * W * 4 + nlab * (2 if mask_u8 is not None else 1)
     if branch == "softmax":
         ws = torch.empty(L.MAX_PARTS * (3 * C + 1), dtype=torch.float32, device=dev)
         coef = torch.empty(4 * C + 4, dtype=torch.float32, device=dev)
-        _call("ustrun_ce_dice_softmax_fwd", _ptr(logits), _ptr(target_u8), _ptr(mask_u8), B, C, H, W, float(ce_w), float(dice_w),
+        _profiled("hbm_ce_dice_pass1", p1_bytes, "ustrun_ce_dice_softmax_fwd", _ptr(logits), _ptr(target_u8), _ptr(mask_u8), B, C, H, W, float(ce_w), float(dice_w),
               _ptr(class_weight), _ptr(ws), _ptr(coef), _ptr(loss3), _stream())
     else:
         ws = torch.empty(L.MAX_PARTS * 4, dtype=torch.float32, device=dev)
         coef = torch.empty(4, dtype=torch.float32, device=dev)
-        _call("ustrun_bce_dice_sigmoid_fwd", _ptr(logits), _ptr(target_u8), _ptr(mask_u8), B, C, H, W, float(ce_w), float(dice_w),
+        _profiled("hbm_ce_dice_pass1", p1_bytes, "ustrun_bce_dice_sigmoid_fwd", _ptr(logits), _ptr(target_u8), _ptr(mask_u8), B, C, H, W, float(ce_w), float(dice_w),
               _ptr(ws), _ptr(coef), _ptr(loss3), _stream())
     return loss3, coef
 
@@ -68,7 +71,8 @@ def term_backward(logits, target_u8, mask_u8, branch, coef, upstream=None, gscal
         out = torch.empty_like(logits)
         accumulate = False
     name = "ustrun_ce_dice_softmax_bwd" if branch == "softmax" else "ustrun_bce_dice_sigmoid_bwd"
-    _call(name, _ptr(logits), _ptr(target_u8), _ptr(mask_u8), B, C, H, W, _ptr(coef), _ptr(upstream), float(gscale), _ptr(out),
+    nlab = B * H * W * (1 if branch == "softmax" else C)
+    _profiled("hbm_ce_dice_pass2", 2 * B * C * H * W * 4 + nlab * (2 if mask_u8 is not None else 1), name, _ptr(logits), _ptr(target_u8), _ptr(mask_u8), B, C, H, W, _ptr(coef), _ptr(upstream), float(gscale), _ptr(out),
           1 if accumulate else 0, _stream())
     return out
 

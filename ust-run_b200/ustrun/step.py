@@ -28,7 +28,7 @@ import torch
 from . import _lib as L
 from . import bridge
 from . import engine as E
-from .engine import _call, _ptr, _stream
+from .engine import _call, _profiled, _ptr, _stream
 from .loss_ops import as_u8, term_backward, term_forward
 from .optim import FusedSGDEMA
 
@@ -63,11 +63,14 @@ def pseudo_labels(t1, t2, t3, box, cut_label, cut_mask, choice, threshold, branc
     ptrs = [_ptr(o) for o in outs]
     if s0 is None:
         ptrs[8] = None
+    # algorithmic bytes: 4 logit tensors (fp32) + box / cut label / cut mask read, 9 uint8 planes written
+    nlab = Bu * H * W * (1 if branch == "softmax" else C)
+    pl_bytes = (4 if s0 is not None else 3) * Bu * C * H * W * 4 + Bu * H * W + 2 * nlab + (9 if s0 is not None else 8) * nlab
     if branch == "softmax":
-        _call("ustrun_pseudo_label_softmax", _ptr(t1), _ptr(t2), _ptr(t3), _ptr(s0), _ptr(box_u8), _ptr(cl), _ptr(cm), _ptr(choice_i),
+        _profiled("hbm_pseudo_label", pl_bytes, "ustrun_pseudo_label_softmax", _ptr(t1), _ptr(t2), _ptr(t3), _ptr(s0), _ptr(box_u8), _ptr(cl), _ptr(cm), _ptr(choice_i),
               float(threshold), Bu, C, H, W, *ptrs, _stream())
     else:
-        _call("ustrun_pseudo_label_sigmoid", _ptr(t1), _ptr(t2), _ptr(t3), _ptr(s0), _ptr(box_u8), _ptr(cl), _ptr(cm), _ptr(choice_i),
+        _profiled("hbm_pseudo_label", pl_bytes, "ustrun_pseudo_label_sigmoid", _ptr(t1), _ptr(t2), _ptr(t3), _ptr(s0), _ptr(box_u8), _ptr(cl), _ptr(cm), _ptr(choice_i),
               float(threshold), float(1 - threshold), Bu, C, H, W, *ptrs, _stream())
     res = dict(zip(names, outs))
     if s0 is None:
