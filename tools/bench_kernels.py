@@ -36,6 +36,8 @@ def act(B, H, W, C):
 
 B, H0 = 8, 384
 ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+# USTRUN_BENCH_STEP_SHAPE="B,H,C": shape of the pseudo-label / CE+Dice section (default: cfg2 = 8,384,2; cfg4 = 32,288,4)
+STEP_SHAPE = [int(v) for v in os.environ.get("USTRUN_BENCH_STEP_SHAPE", "8,384,2").split(",")]
 if ONLY == "narrow":
     layers_skip = True
 else:
@@ -95,7 +97,8 @@ sc4 = torch.empty(4 * 64, device="cuda"); pr = torch.rand(148 * 128, device="cud
 gam = torch.ones(64, device="cuda"); rm = torch.zeros(64, device="cuda"); rv = torch.ones(64, device="cuda"); nbt = torch.zeros(1, dtype=torch.int64, device="cuda")
 report("bn_finalize (148 partial rows)", timeit(lambda: E._call("ustrun_bn_finalize", E._ptr(pr), 148, 64, float(npx), E._ptr(gam), E._ptr(rm), None, E._ptr(rm), E._ptr(rv), E._ptr(nbt), 0.1, 1e-5, 1, E._ptr(sc4[:64]), E._ptr(sc4[64:128]), E._ptr(sc4[128:192]), E._ptr(sc4[192:]), None, S())))
 # ---- step kernels ----
-C = 2
+B, H, C = STEP_SHAPE
+npx = B * H * H
 t = [torch.randn(B, C, H, H, device="cuda") * 3 for _ in range(4)]
 box = (torch.rand(B, H, H, device="cuda") > 0.7).to(torch.uint8)
 cl = torch.randint(0, C, (B, H, H), device="cuda", dtype=torch.uint8); cm = torch.ones(B, H, H, device="cuda", dtype=torch.uint8)
