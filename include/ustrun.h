@@ -263,6 +263,31 @@ int ustrun_fft_amp_mix(const float* src, const float* trg, const double* ratio, 
 int ustrun_hardness(const unsigned char* stu_pl, const unsigned char* tea_pl, int B, int H, int W, int mode, int first_epoch,
                     unsigned int* workspace, double* hardness, double* dice, int* lq_idx, void* stream);
 
+/* ---- confidence bank / low-quality sample bookkeeping (second half) --------------
+ * Replaces the host-side numpy / torch.cat code of train.py:754-781 (bank FIFO + adaptive threshold), :612-626 (CutMix partner
+ * pool and choice), :741-743 (hardest sample) and obtain_all_cover_box :242-251.  The bank length (int) and choice_th (double)
+ * are DEVICE scalars; nothing is copied to the host.
+ * ustrun_bank_update: simple_ulb_idx = hardness < choice_th; new bank = selected samples of this batch (batch order) followed by
+ *   the first `newlen` old entries (newlen = max_len - cur if n + cur > max_len else n); choice_th = min(choice_th, max hardness
+ *   in the new bank) if something was selected, else min(increase * choice_th, 0.1) (unchanged while the bank is empty).
+ *   old_* / new_* are the two copies of the bank storage (max_len slots of img_elems floats / lab_elems bytes); new_hard /
+ *   old_hard double[max_len]; plan_ws int[max_len + 1].  Requires Bu <= max_len.
+ * ustrun_bank_choice: choice[i] (train.py:615,621-625) from host draws r_lb[i] in [0, Bl), r_u[i] in [0, 1), perm (a permutation
+ *   of 0..Bu-1) and the device-side bank length: first Bu - k partners from the labelled batch, k = min(Bu / 2, n) from the bank
+ *   (index Bl + floor(r_u * n)), permuted.
+ * ustrun_lq_select: copies sample *lq_idx (device int, from ustrun_hardness) of the batch into the lq buffers.
+ * ustrun_cover_box: box[H][W] = 1 inside the bounding box of the union of the non-zero pixels of up to four uint8 planes
+ *   (nullable); if the union is empty the box is `fallback` (a host-drawn CutMix rectangle, train.py:245) or all zero. */
+int ustrun_bank_update(const double* hardness, int Bu, const float* batch_img, const unsigned char* batch_pl, const unsigned char* batch_mask,
+                       const float* old_img, const unsigned char* old_pl, const unsigned char* old_mask, const double* old_hard, float* new_img,
+                       unsigned char* new_pl, unsigned char* new_mask, double* new_hard, int* n_state, double* th_state, int max_len, double increase,
+                       long long img_elems, long long lab_elems, int* plan_ws, void* stream);
+int ustrun_bank_choice(const int* n_state, int Bl, int Bu, const int* r_lb, const double* r_u, const int* perm, int* choice, void* stream);
+int ustrun_lq_select(const int* lq_idx, const float* img, const unsigned char* pl, const unsigned char* mask, float* out_img, unsigned char* out_pl,
+                     unsigned char* out_mask, long long img_elems, long long lab_elems, void* stream);
+int ustrun_cover_box(const unsigned char* p0, const unsigned char* p1, const unsigned char* p2, const unsigned char* p3, int H, int W,
+                     const unsigned char* fallback, unsigned char* box, void* stream);
+
 /* ---- evaluation helpers --------------------------------------------------
  * ustrun_encode_labels: the label encodings of train.py:590-608 / :281-288 and train_mnms.py:549-556 on the float32
  *   label image the data loader yields.  mode 0: y == 0 (prostate); 1: y == 255 (BUSI); 2: two planes {y == 0, y <= 128}

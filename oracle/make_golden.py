@@ -561,6 +561,116 @@ def case_eval():
     print(f"eval: reference lines train.py:{enc_at[0]}-{enc_at[1]}, :{pred_at[0]}-{pred_at[1]}, train_mnms.py:{mnms_at[0]}-{mnms_at[1]} == oracle on 4 datasets")
 
 
+def case_bank():
+    """Confidence-bank bookkeeping (train.py:612-625, 720-743, 745-779) and ``obtain_all_cover_box`` (train.py:242-251): the
+    reference's own lines, sliced out of train.py and executed unmodified on CPU tensors (``.cuda()`` is a no-op here, host RNG
+    calls replay recorded draws), vs oracle/bank_ref.py."""
+    import ast
+    from oracle import bank_ref as Bk
+    upd_src, upd_at = _reference_lines("train.py", "simple_ulb_idx = hardness < choice_th", "assert len(simple_ulb) == len(cor_pl)", after="for i_batch")
+    pool_src, pool_at = _reference_lines("train.py", "if simple_ulb is None or len(simple_ulb) == 0:", "mix_img = cut_img[choice]", after="with amp_cm():")
+    lq_src, lq_at = _reference_lines("train.py", "if args.dataset == 'fundus':", "logits_lq_s = model(lq_s)", after="new_choice = np.random.randint(0, len(lb_x_w))")
+    src = open(os.path.join(REF, "train.py")).read()
+    tree = ast.parse(src)
+    box_code = "\n\n".join(ast.get_source_segment(src, n) for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("obtain_all_cover_box", "obtain_cutmix_box"))
+    saved_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        class _Args:
+            increase, dataset = 1.0005, "prostate"
+
+        class _NpRandom:
+            draws = {}
+
+            @classmethod
+            def randint(cls, lo, hi, n=None):
+                if lo == 0:
+                    return np.asarray(cls.draws["r_lb"][:n], dtype=np.int64)
+                nb = hi - lo
+                return lo + np.floor(np.asarray(cls.draws["r_u"][:n], dtype=np.float64) * nb).astype(np.int64)
+
+            @classmethod
+            def permutation(cls, x):
+                return np.asarray(x)[np.asarray(cls.draws["perm"])]
+
+        class _Np:
+            random = _NpRandom
+            concatenate = staticmethod(np.concatenate)
+
+        rng = np.random.RandomState(SEED + 31)
+        g = torch.Generator().manual_seed(SEED + 31)
+        fx = {"src/update_lines": np.asarray(upd_at), "src/pool_lines": np.asarray(pool_at), "src/lq_lines": np.asarray(lq_at)}
+        for ds, C, k in (("prostate", 1, 2), ("fundus", 3, 2)):
+            Bl = Bu = 4
+            H = W = 16
+            max_len = 6
+            ref = dict(simple_ulb=None, cor_pl=None, cor_gt=None, cor_hardness=[], cor_dc=None, cor_mask=None, choice_th=0.1)
+            st = Bk.new_state()
+            # hardness scripts: nothing selected / some / all (overflow) / none again (threshold grows) ...
+            script = [[0.5, 0.2, 0.3, 0.9], [0.05, 0.5, 0.02, 0.7], [0.01, 0.015, 0.5, 0.012], [0.3, 0.3, 0.3, 0.3], [0.001, 0.002, 0.003, 0.004],
+                      [0.0005, 0.9, 0.0007, 0.0001], [0.5, 0.5, 0.5, 0.5], [0.00005, 0.00001, 0.5, 0.00002]]
+            for step, hs in enumerate(script):
+                hardness = np.asarray(hs, dtype=np.float64)
+                ulb_x_w = torch.rand(Bu, C, H, W, generator=g) * 2 - 1
+                lb_x_w = torch.rand(Bl, C, H, W, generator=g) * 2 - 1
+                if ds == "fundus":
+                    pseudo_label = torch.randint(0, 2, (Bu, 2, H, W), generator=g).float()
+                    mask = torch.randint(0, 2, (Bu, 2, H, W), generator=g).float()
+                    lb_mask = torch.randint(0, 2, (Bl, 2, H, W), generator=g).float()
+                    lb_mask_shape = (Bl, 2, H, W)
+                else:
+                    pseudo_label = torch.randint(0, k, (Bu, H, W), generator=g)
+                    mask = torch.randint(0, 2, (Bu, 1, H, W), generator=g).float()
+                    lb_mask = torch.randint(0, k, (Bl, H, W), generator=g)
+                    lb_mask_shape = (Bl, 1, H, W)
+                # ---- pool + choice BEFORE the update (train.py:612-625), with the bank of the previous step
+                n_bank = 0 if ref["simple_ulb"] is None else len(ref["simple_ulb"])
+                draws = {"r_lb": rng.randint(0, Bl, Bu), "r_u": rng.uniform(0, 1, Bu), "perm": rng.permutation(Bu)}
+                _NpRandom.draws = draws
+                ns = dict(simple_ulb=ref["simple_ulb"], cor_pl=ref["cor_pl"], cor_mask=ref["cor_mask"], lb_x_w=lb_x_w, lb_mask=lb_mask, lb_mask_shape=lb_mask_shape,
+                          ulb_x_s=ulb_x_w, torch=torch, np=_Np)
+                exec(compile(pool_src, "train.py", "exec"), ns)
+                ci, cl, cm = Bk.cut_pool(st, lb_x_w, lb_mask, lb_mask_shape)
+                assert torch.equal(ns["cut_img"], ci) and torch.equal(ns["cut_label"], cl) and torch.equal(ns["cut_mask"], cm), f"bank oracle: pool differs ({ds}, step {step})"
+                ch = Bk.draw_choice(n_bank, Bl, Bu, draws["r_lb"], draws["r_u"], draws["perm"])
+                assert np.array_equal(np.asarray(ns["choice"]), ch), f"bank oracle: choice differs ({ds}, step {step})"
+                # ---- update (train.py:745-779)
+                a = _Args(); a.dataset = ds
+                ns = dict(hardness=hardness, choice_th=ref["choice_th"], simple_ulb=ref["simple_ulb"], cor_pl=ref["cor_pl"], cor_gt=ref["cor_gt"], cor_hardness=ref["cor_hardness"],
+                          cor_dc=ref["cor_dc"], cor_mask=ref["cor_mask"], ulb_x_w=ulb_x_w, pseudo_label=pseudo_label, ulb_mask=pseudo_label, ulb_dc=torch.arange(Bu), mask=mask,
+                          max_len=max_len, args=a, torch=torch, np=np)
+                exec(compile(upd_src, "train.py", "exec"), ns)
+                for key in ("simple_ulb", "cor_pl", "cor_gt", "cor_hardness", "cor_dc", "cor_mask", "choice_th"):
+                    ref[key] = ns[key]
+                st = Bk.bank_update(st, hardness, ulb_x_w, pseudo_label, mask, max_len=max_len, increase=a.increase)
+                assert st["choice_th"] == ref["choice_th"], (ds, step, st["choice_th"], ref["choice_th"])
+                assert torch.equal(st["simple_ulb"], ref["simple_ulb"]) and torch.equal(st["cor_pl"], ref["cor_pl"]) and torch.equal(st["cor_mask"], ref["cor_mask"])
+                assert np.array_equal(st["cor_hardness"], np.asarray(ref["cor_hardness"]))
+                t = f"{ds}/{step}"
+                fx[t + "/hardness"], fx[t + "/ulb_x_w"], fx[t + "/lb_x_w"] = hardness, np_(ulb_x_w), np_(lb_x_w)
+                fx[t + "/pseudo_label"], fx[t + "/mask"], fx[t + "/lb_mask"] = np_(pseudo_label).astype(np.uint8), np_(mask).astype(np.uint8), np_(lb_mask).astype(np.uint8)
+                fx[t + "/r_lb"], fx[t + "/r_u"], fx[t + "/perm"], fx[t + "/choice"] = draws["r_lb"], draws["r_u"], draws["perm"], np.asarray(ns_choice := ch)
+                fx[t + "/n_bank_after"], fx[t + "/choice_th_after"] = np.int64(len(ref["simple_ulb"])), np.float64(ref["choice_th"])
+                fx[t + "/bank_img"], fx[t + "/bank_pl"], fx[t + "/bank_mask"] = np_(ref["simple_ulb"]), np_(ref["cor_pl"]).astype(np.uint8), np_(ref["cor_mask"]).astype(np.uint8)
+                fx[t + "/bank_hardness"] = np.asarray(ref["cor_hardness"], dtype=np.float64)
+                # ---- low-quality sample CutMix with the previous pseudo label (train.py:720-738)
+                lq_idx = int(np.argmax(hardness))
+                lq_u, lq_pl, lq_mask = ulb_x_w[[lq_idx]].clone(), pseudo_label[[lq_idx]].clone(), mask[[lq_idx]].clone()
+                new_choice = int(rng.randint(0, Bl))
+                boxns = {"torch": torch, "np": np, "random": __import__("random")}
+                exec(compile(box_code, "train.py", "exec"), boxns)
+                ns = dict(args=a, lq_pl=lq_pl, lb_mask=lb_mask, new_choice=new_choice, obtain_all_cover_box=boxns["obtain_all_cover_box"], lq_u=lq_u, lb_x_w=lb_x_w, lq_mask=lq_mask, torch=torch)
+                if bool((Bk.lq_region(lq_pl, lb_mask, new_choice, ds) != 0).any()):
+                    exec(compile(lq_src, "train.py", "exec"), ns)
+                    lq_s, pl_lq, m_lq, box = Bk.lq_compose(lq_u, lq_pl, lq_mask, lb_x_w, lb_mask, new_choice, ds)
+                    assert torch.equal(ns["lq_s"], lq_s) and torch.equal(ns["pseudo_label_lq"], pl_lq) and torch.equal(ns["mask_lq"], m_lq), f"bank oracle: lq compose differs ({ds}, step {step})"
+                    fx[t + "/lq_new_choice"], fx[t + "/lq_idx"], fx[t + "/lq_s"], fx[t + "/lq_box"] = np.int64(new_choice), np.int64(lq_idx), np_(lq_s), np_(box).astype(np.uint8)
+        np.savez_compressed(os.path.join(OUT, "bank.npz"), **fx)
+        print(f"bank: reference lines train.py:{upd_at[0]}-{upd_at[1]}, :{pool_at[0]}-{pool_at[1]}, :{lq_at[0]}-{lq_at[1]} == oracle on 2 datasets x 8 steps")
+    finally:
+        torch.Tensor.cuda = saved_cuda
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -573,12 +683,16 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "eval":
         case_eval()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "bank":
+        case_bank()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "dsbn":
         case_unet_b_dsbn()
         case_step_dsbn()
         return
     case_fft_mix()
     case_hardness()
+    case_bank()
     case_eval()
     case_losses()
     case_unet_a(1, 2, 32, 2)

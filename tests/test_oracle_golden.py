@@ -260,3 +260,30 @@ def test_eval_oracle_reproduces_reference_fixture():
         assert np.allclose(dice, fx[f"{ds}/dice"], rtol=4e-16, atol=0), ds
         assert np.array_equal(dc, fx[f"{ds}/dc"]) and np.array_equal(jc, fx[f"{ds}/jc"]), ds
     assert float(fx["fundus/dice_per_sample"][0, 0]) < 0.05          # the all-background prediction of sample 0
+
+
+def test_bank_oracle_reproduces_reference_fixture():
+    """oracle/bank_ref.py against tests/golden/bank.npz (outputs of the reference's own lines train.py:754-781, :612-626, :722-739
+    and obtain_all_cover_box :242-251, executed by oracle/make_golden.py::case_bank)."""
+    from oracle import bank_ref as Bk
+    fx = np.load(os.path.join(GOLDEN, "bank.npz"))
+    for ds in ("prostate", "fundus"):
+        st = Bk.new_state()
+        for step in range(8):
+            p = f"{ds}/{step}"
+            t = lambda k: torch.from_numpy(fx[p + "/" + k])
+            n_bank = 0 if st["simple_ulb"] is None else len(st["simple_ulb"])
+            ch = Bk.draw_choice(n_bank, 4, 4, fx[p + "/r_lb"], fx[p + "/r_u"], fx[p + "/perm"])
+            assert np.array_equal(ch, fx[p + "/choice"])
+            mask = t("mask").float()
+            pl = t("pseudo_label").float() if ds == "fundus" else t("pseudo_label").long()
+            st = Bk.bank_update(st, fx[p + "/hardness"], t("ulb_x_w"), pl, mask, max_len=6, increase=1.0005)
+            assert len(st["simple_ulb"]) == int(fx[p + "/n_bank_after"]) and st["choice_th"] == float(fx[p + "/choice_th_after"])
+            assert np.array_equal(st["simple_ulb"].numpy(), fx[p + "/bank_img"]) and np.array_equal(st["cor_hardness"], fx[p + "/bank_hardness"])
+            assert np.array_equal(st["cor_pl"].numpy().astype(np.uint8), fx[p + "/bank_pl"]) and np.array_equal(st["cor_mask"].numpy().astype(np.uint8), fx[p + "/bank_mask"])
+            if (p + "/lq_s") in fx.files:
+                i, nc = int(fx[p + "/lq_idx"]), int(fx[p + "/lq_new_choice"])
+                lbm = t("lb_mask").float() if ds == "fundus" else t("lb_mask").long()
+                lq_s, _, _, box = Bk.lq_compose(t("ulb_x_w")[[i]], pl[[i]], mask[[i]], t("lb_x_w"), lbm, nc, ds)
+                assert np.array_equal(lq_s.numpy(), fx[p + "/lq_s"]) and np.array_equal(box.numpy().astype(np.uint8), fx[p + "/lq_box"])
+        assert float(fx[f"{ds}/7/choice_th_after"]) < 0.1 and int(fx[f"{ds}/2/n_bank_after"]) >= 3

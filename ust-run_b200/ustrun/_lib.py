@@ -74,6 +74,10 @@ _SIGS = {
     "ustrun_sgd_ema_multi_dev": [p, p, p, i32, p, f32, f32, i32, i32, p],
     "ustrun_fft_amp_mix": [p, p, p, f64, p, i32, i32, i32, i32, p, i64, p],
     "ustrun_hardness": [p, p, i32, i32, i32, i32, i32, p, p, p, p, p],
+    "ustrun_bank_update": [p, i32, p, p, p, p, p, p, p, p, p, p, p, p, p, i32, f64, i64, i64, p, p],
+    "ustrun_bank_choice": [p, i32, i32, p, p, p, p, p],
+    "ustrun_lq_select": [p, p, p, p, p, p, p, i64, i64, p],
+    "ustrun_cover_box": [p, p, p, p, i32, i32, p, p, p],
     "ustrun_encode_labels": [p, i32, i32, i32, i32, p, p],
     "ustrun_predict": [p, i32, i32, i32, i32, i32, p, p],
     "ustrun_seg_metrics": [p, p, i32, i32, i32, i32, p, p, p],

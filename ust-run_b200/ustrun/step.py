@@ -267,6 +267,9 @@ class SSLTrainer:
         if "domain_lb" in batch or "domain_ulb" in batch:
             domains = step_domains(int(batch["domain_lb"]), int(batch["domain_ulb"]))
         tensors = {k: v for k, v in batch.items() if isinstance(v, torch.Tensor)}
+        if lq is not None and not isinstance(lq, torch.Tensor):       # (lq_u, labelled image, box): ConfidenceBank.lq_input
+            tensors["_lq_u"], tensors["_lq_img"], tensors["_lq_box"] = lq[0], lq[1], as_u8(lq[2])
+            lq = None
         if "mix_ratio" in batch and "mix_ratio" not in tensors:       # host floats (train.py:180) -> one float64 per sample
             tensors["mix_ratio"] = torch.as_tensor(batch["mix_ratio"], dtype=torch.float64)
         key = None
@@ -359,8 +362,10 @@ class SSLTrainer:
                 lambda: self._branch(mix_input(b["ulb_s"], b["move_transx"], box_u8), comp["pseudo_label_ul"], comp["mask_ul"], H_CW, "ul"),
                 lambda: self._branch(mix_input(b["move_transx"], b["ulb_s"], box_u8), comp["pseudo_label_lu"], comp["mask_lu"], H_CW, "lu"),
                 lambda: self._last_branch_job(mix_input(b["ulb_s"], None, None), comp["pseudo_label_w"], comp["mask_w"])]
-        if lq is not None:
-            jobs.append(lambda: self._forward(self.model, mix_input(lq, None, None), False, "lq")[1])
+        if lq is not None or "_lq_u" in b:
+            # lq: the image itself, or (lq_u, labelled image, box) = the CutMix of train.py:731 composed by the input kernel
+            lq_mix = (lq, None, None) if lq is not None else (b["_lq_u"], b["_lq_img"], b["_lq_box"].contiguous())
+            jobs.append(lambda: self._forward(self.model, mix_input(*lq_mix), False, "lq")[1])
         res = self._run_jobs(jobs)
         (l_sup, lg_lb), (l_ul, lg_ul), (l_lu, lg_lu), (l_s, lg_s) = res[:4]
         if multi:
