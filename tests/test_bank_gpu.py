@@ -22,6 +22,7 @@ def test_bank_sequence_matches_reference_lines(ds, C, lab_c):
     H = W = 16
     bank = ConfidenceBank(Bl, Bu, C, H, W, label_channels=lab_c, max_len=6, increase=1.0005)
     t = lambda k: torch.from_numpy(fx[k]).cuda()
+    L_ = H * W * (lab_c or 1)
     n_prev = 0
     for step in range(8):
         p = f"{ds}/{step}"
@@ -36,8 +37,8 @@ def test_bank_sequence_matches_reference_lines(ds, C, lab_c):
         if step > 0:
             q = f"{ds}/{step - 1}"
             n = int(fx[q + "/n_bank_after"])
-            assert torch.equal(cut_img[Bl:Bl + n], t(q + "/bank_img")) and torch.equal(cut_label[Bl:Bl + n].reshape(n, -1), t(q + "/bank_pl").reshape(n, -1))
-            assert torch.equal(cut_mask[Bl:Bl + n].reshape(n, -1), t(q + "/bank_mask").reshape(n, -1))
+            assert torch.equal(cut_img[Bl:Bl + n], t(q + "/bank_img")) and torch.equal(cut_label[Bl:Bl + n].reshape(n, L_), t(q + "/bank_pl").reshape(n, L_))
+            assert torch.equal(cut_mask[Bl:Bl + n].reshape(n, L_), t(q + "/bank_mask").reshape(n, L_))
         # low-quality sample of this batch and its CutMix box / image
         if (p + "/lq_s") in fx.files:
             lq_idx = torch.tensor([int(fx[p + "/lq_idx"])], dtype=torch.int32, device="cuda")
@@ -55,7 +56,7 @@ def test_bank_sequence_matches_reference_lines(ds, C, lab_c):
         assert int(n_dev) == n, (step, int(n_dev), n)
         assert float(th) == float(fx[p + "/choice_th_after"]), (step, float(th), float(fx[p + "/choice_th_after"]))
         assert torch.equal(b_img[:n], t(p + "/bank_img"))
-        assert torch.equal(b_pl[:n].reshape(n, -1), t(p + "/bank_pl").reshape(n, -1)) and torch.equal(b_mask[:n].reshape(n, -1), t(p + "/bank_mask").reshape(n, -1))
+        assert torch.equal(b_pl[:n].reshape(n, L_), t(p + "/bank_pl").reshape(n, L_)) and torch.equal(b_mask[:n].reshape(n, L_), t(p + "/bank_mask").reshape(n, L_))
         assert np.array_equal(b_hard[:n].cpu().numpy(), fx[p + "/bank_hardness"])
         n_prev = n
 
