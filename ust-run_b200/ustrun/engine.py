@@ -667,7 +667,7 @@ def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
     wf, wd = packed.get(up.weight, transposed=True, need_wd=ctx.need_grad or up.weight.requires_grad)
     cin, cout = up.in_channels, up.out_channels
     impl = _impl_for(cin, cout, x.dtype_code)
-    tcls = "tc_conv" if impl == L.TCGEN05 else "simt_conv"
+    tcls = "tc_convT" if impl == L.TCGEN05 else "simt_conv"
     tflops = 2.0 * x.npix * cin * cout * 4
     _profiled(tcls, tflops, "ustrun_convT2x2_fwd", impl, x.ptr, x.ld, _ptr(wf), _ptr(up.bias), out.ptr, out.ld, x.dtype_code, x.B, x.H, x.W, cin, cout, _stream(),
               meta=(x.B, x.H, x.W, cin, cout, "T"))
@@ -683,7 +683,7 @@ def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
                 dw, acc = sink.get(up.weight)
                 nbytes = L.lib.ustrun_conv_wgrad_workspace_bytes(impl, x.B, x.H, x.W, cin, cout, 2)
                 ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
-                _profiled("tc_wgrad" if impl == L.TCGEN05 else "simt_wgrad", tflops, "ustrun_convT2x2_wgrad", impl, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code,
+                _profiled("tc_wgradT" if impl == L.TCGEN05 else "simt_wgrad", tflops, "ustrun_convT2x2_wgrad", impl, G.ptr, G.ld, x.ptr, x.ld, _ptr(dw), acc, x.dtype_code,
                           x.B, x.H, x.W, cin, cout, _ptr(ws), int(nbytes), _stream(), meta=(x.B, x.H, x.W, cin, cout, "T"))
                 sink.done(up.weight)
             on_side_stream(wgrad_fn, (G.t, x.t))
