@@ -133,3 +133,33 @@ def test_multi_lane_step_is_bit_identical(kind, c, k, hw, branch, lanes, graph, 
         assert torch.equal(a, b)
     for n in b0:
         assert torch.equal(b0[n], b1[n]), n
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_upload_prefetch_equals_direct_step(graph):
+    """``trainer.upload(host batch)`` (copy stream, two staging sets) + ``step`` == ``step`` on device tensors, bit for bit."""
+    from ustrun import synth as S
+    from ustrun.step import SSLTrainer
+    s, t = _pair("a", 1, 2)
+    s2, t2 = _pair("a", 1, 2)
+    tr = SSLTrainer(s, t, n_classes=2, threshold=0.6, use_graph=graph, lanes=2)
+    tr2 = SSLTrainer(s2, t2, n_classes=2, threshold=0.6)
+
+    def host(i):
+        h = S.synthetic_batch(1, 2, 64, 64, 2, 2, seed=40 + i)
+        for kk in ("lb_mask", "cut_label", "cut_mask", "box"):
+            h[kk] = h[kk].to(torch.uint8)
+        h["choice"] = h["choice"].to(torch.int32)
+        return {kk: v.contiguous().pin_memory() for kk, v in h.items()}
+
+    batches = [host(i) for i in range(6)]
+    nxt = tr.upload(batches[0], lq=batches[0]["ulb_w"][:1])
+    for i in range(6):
+        cur = nxt
+        a = tr.step(cur)
+        if i + 1 < 6:
+            nxt = tr.upload(batches[i + 1], lq=batches[i + 1]["ulb_w"][:1])
+        b = tr2.step({kk: v.cuda() for kk, v in batches[i].items()}, lq=batches[i]["ulb_w"][:1].cuda())
+        assert torch.equal(a["loss"], b["loss"]), i
+    for p, q in zip(s.parameters(), s2.parameters()):
+        assert torch.equal(p, q)

@@ -149,6 +149,7 @@ class SSLTrainer:
         self._graphs = {}
         self._eager_steps = 0
         self._eager_by_key = {}
+        self._copy_stream, self._up_slot, self._staging, self._consumed = None, 0, [{}, {}], [None, None]
         self.launches_per_step = 0            # kernels of the last eager / captured step (bench.py: gpu_launches)
         self._domains = None
 
@@ -240,6 +241,40 @@ class SSLTrainer:
         self._hyper_ev[slot] = ev
         return cw
 
+    # -- input prefetch ------------------------------------------------------------------------------------------------
+    def upload(self, batch, lq=None):
+        """Start the host-to-device copy of a (pinned) host batch on the trainer's copy stream and return the batch to pass
+        to ``step``: called right after ``step(i)`` was issued, the upload of step i+1 overlaps step i's kernels (the reference
+        copies synchronously, train.py:582-589).  Two staging sets alternate; ``step`` waits for the copy's event, not for the
+        host."""
+        dev = self.hyper.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        slot = self._up_slot
+        self._up_slot ^= 1
+        items = dict(batch)
+        if lq is not None:
+            items["_lq_plain"] = lq
+        bufs = self._staging[slot]
+        for k, v in items.items():
+            if isinstance(v, torch.Tensor) and (k not in bufs or bufs[k].shape != v.shape or bufs[k].dtype != v.dtype):
+                bufs[k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
+        st = self._copy_stream
+        if self._consumed[slot] is not None:
+            st.wait_event(self._consumed[slot])                 # the step that read this staging set has been issued and must finish first
+        out = {}
+        with torch.cuda.stream(st):
+            for k, v in items.items():
+                if isinstance(v, torch.Tensor):
+                    bufs[k].copy_(v, non_blocking=True)
+                    out[k] = bufs[k]
+                else:
+                    out[k] = v
+            ev = torch.cuda.Event()
+            ev.record(st)
+        out["_ustrun_ready"] = (ev, slot)
+        return out
+
     # -- checkpointing (utils/util.py:259-297 saves the optimizer state; train.py:542-548 restores it and iter_num) ----------
     def state_dict(self):
         return {"optimizer": self.opt.state_dict(), "iter_num": self.iter_num, "lr": self.lr}
@@ -260,6 +295,12 @@ class SSLTrainer:
         Returns device tensors (losses, compositions); nothing is copied to the host.  With ``use_graph`` the returned
         tensors are the graph's static outputs: read them before the next ``step``."""
         it = self.iter_num
+        ready = batch.get("_ustrun_ready")
+        if ready is not None:                       # inputs staged by upload(): wait for the copy on the device, not on the host
+            torch.cuda.current_stream().wait_event(ready[0])
+            if lq is None:
+                lq = batch.get("_lq_plain")
+            batch = {k: v for k, v in batch.items() if k not in ("_ustrun_ready", "_lq_plain")}
         if self.dp is not None and getattr(self.dp, "peer", None) is not None:
             self.dp.peer.poll()                     # a peer-BN timeout of an earlier step raises here (one step late, no sync)
         gscale = 1.0 if self.dp is None else (1.0 if self.dp.global_loss else 1.0 / self.dp.world)
@@ -289,6 +330,10 @@ class SSLTrainer:
             self._eager_steps += 1
             if key is not None:
                 self._eager_by_key[key] = self._eager_by_key.get(key, 0) + 1
+        if ready is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._consumed[ready[1]] = ev
         # the reference's lr schedule (train.py:854-858)
         self.lr = self.base_lr * (1.0 - it / self.max_iterations) ** 0.9
         self.iter_num = it + 1
