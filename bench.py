@@ -157,7 +157,8 @@ def run_ours(args):
     student, teacher = make_models(model_name, c, k)
     student, teacher = student.cuda().train(), teacher.cuda().train()
     use_graph = args.graph == "on" or (args.graph == "auto" and (dp is None or dp.graph_safe) and args.workload != "cfg5")
-    lanes = args.lanes if args.lanes > 0 else (1 if (dp is not None or args.workload == "cfg5") else 4)
+    # auto: the tensor-bound UNet-A gains from 2 lanes (4 thrash the L2), the latency-bound UNet-B from 4
+    lanes = args.lanes if args.lanes > 0 else (1 if (dp is not None or args.workload == "cfg5") else (2 if model_name.startswith("unet_a") else 4))
     trainer = SSLTrainer(student, teacher, n_classes=k, branch=branch, base_lr=0.03, max_iterations=60000, threshold=0.95, dp=dp, use_graph=use_graph,
                          lanes=lanes)
     trainer.iter_num = 30000                      # mid-training: consistency weight 1.0, alpha 0.99
@@ -200,14 +201,25 @@ def run_ours(args):
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
     staged = [trainer.upload({**pinned, **extra}, lq=lq_pinned)]
+    loss_ring = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev, loss_seen = [None, None], []
 
     def step_e2e():
-        # the public calls with HOST (pinned) inputs: step() consumes the batch upload() staged, then the NEXT step's inputs are
-        # uploaded on the copy stream while this step's kernels run (one upload of h2d_bytes and one loss read per step)
+        # the public calls with HOST (pinned) inputs, software-pipelined like an input pipeline with asynchronous logging:
+        # step() consumes the batch upload() staged; the NEXT step's inputs are uploaded on the copy stream while this step's
+        # kernels run; this step's loss is copied to pinned memory behind its kernels and READ on the host one step later (the
+        # host blocks on that copy's event), so the host never idles the GPU.  Per timed step: one upload of h2d_bytes, one loss read.
+        i = len(loss_seen) & 1
         out = trainer.step(staged[0])
         staged[0] = trainer.upload({**pinned, **extra}, lq=lq_pinned)
-        loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()        # the user reads the loss every step
+        loss_ring[i].copy_(out["loss"].reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        if loss_ev[i ^ 1] is not None:
+            loss_ev[i ^ 1].synchronize()                 # the previous step's loss has landed: the user reads it now
+            loss_host.copy_(loss_ring[i ^ 1])
+        loss_ev[i] = ev
+        loss_seen.append(1)
         return out
 
     dp_parity = dp_parity_record(args, dp, rank, world) if (world > 1 and not args.no_dp_parity) else None
@@ -302,7 +314,7 @@ def run_ours(args):
                        "cuda_graph": bool(use_graph), "lanes": trainer.lanes, "dsbn_domains": list(DSBN_DOMAINS) if dsbn else None,
                        "sync_bn": (False if (world == 1 or args.no_sync_bn) else ("peer" if dp is not None and dp.peer is not None else "nccl"))},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "how": "trainer.upload(pinned host batch) + trainer.step(): every timed step uploads one batch (the next step's, on a copy stream, overlapping this step's kernels) and reads this step's loss back to the host"},
+                    "how": "trainer.upload(pinned host batch) + trainer.step(), software-pipelined: every timed step uploads one batch (the next step's, on a copy stream, overlapping this step's kernels) and reads one loss on the host (the previous step's: the host blocks on that D2H copy's event, not on the whole stream)"},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "parity": parity,
             "dp_parity": dp_parity}
     print(json.dumps(line))

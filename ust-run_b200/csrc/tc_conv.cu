@@ -178,7 +178,9 @@ struct TcConvParams {
   int halves, units;     // halves == 2: an M tile is two independent TW x TH (<= 64 pixel) boxes, rows 0-63 / 64-127;
                          // units = number of boxes (= m_tiles when halves == 1)
   float* partials;       // [ctas_per_n][2][Cout] or null
-  const float* bias;     // [Cout] or null
+  const float* bias;     // [Cout] or null ([out_split] when out_split > 0)
+  int out_split;         // > 0: the N dimension is `Cout / out_split` output tensors of out_split channels each (fused
+                         // ConvTranspose2d: column block t goes to tensor map mapO<t>, bias index = column % out_split)
   int stages, nstaging;  // depth of the TMA ring / number of 16 KB store staging buffers
   uint32_t wres_bytes;   // RESB only: bytes of the resident weight block (ntaps * Cin/64 slots of BN x 128 B)
 };
@@ -219,6 +221,7 @@ template <int BN, bool ROW, bool RESB>
 __global__ void __launch_bounds__(384, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
           const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
+          const __grid_constant__ CUtensorMap mapO1, const __grid_constant__ CUtensorMap mapO2, const __grid_constant__ CUtensorMap mapO3,
           const TcConvParams p) {
   using Cfg = FwdCfg<BN, ROW>;
   const int S = p.stages;          // ring depth and store-staging buffers: chosen on the host (launch_fwd)
@@ -416,10 +419,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c32 * 32), v);
           uint32_t packed[16];
+          const int bcol = p.out_split > 0 ? (n0 + c32 * 32) % p.out_split : n0 + c32 * 32;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float a = v[2 * i], c = v[2 * i + 1];
-            if (p.bias) { a += p.bias[n0 + c32 * 32 + 2 * i]; c += p.bias[n0 + c32 * 32 + 2 * i + 1]; }
+            if (p.bias) { a += p.bias[bcol + 2 * i]; c += p.bias[bcol + 2 * i + 1]; }
             __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
             packed[i] = *reinterpret_cast<uint32_t*>(&h);
           }
@@ -449,8 +453,15 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         named_bar_sync(kEpiBar1, 128);
         if (q == 0) {                 // bulk-group state is per thread: elect.sync picks the same lane for the same mask every time
           if (elect_one()) {
-            tma_store_4d(&mapO, stg, n0 + c64 * 64, s0.w0, s0.h0, s0.b);
-            if (two) tma_store_4d(&mapO, stg + kStageA / 2, n0 + c64 * 64, s1.w0, s1.h0, s1.b);
+            int ocol = n0 + c64 * 64;
+            const CUtensorMap* mo = &mapO;
+            if (p.out_split > 0) {                 // fused transposed conv: 64-channel block -> (tap, channel) of the 2x up-sampled grid
+              const int t = ocol / p.out_split;
+              ocol -= t * p.out_split;
+              mo = t == 0 ? &mapO : (t == 1 ? &mapO1 : (t == 2 ? &mapO2 : &mapO3));
+            }
+            tma_store_4d(mo, stg, ocol, s0.w0, s0.h0, s0.b);
+            if (two) tma_store_4d(mo, stg + kStageA / 2, ocol, s1.w0, s1.h0, s1.b);
             tma_store_commit();
           }
           __syncwarp();
@@ -922,10 +933,12 @@ static int plan_fwd_tiles(TcConvParams& p, int B, int H, int W, int Cout) {
   return best_bn;
 }
 
+static const ActView* g_extra_outs = nullptr;      // fused transposed conv: output tensors of taps 1..3 (set around the launch by tc_convT_fwd)
+
 template <int BN, bool ROW, bool RESB>
 static int launch_fwd_impl(const ActView* a, int nmaps, const void* w, long long Ktot, const ActView& out, TcConvParams p, uint32_t smem_bytes,
                            cudaStream_t st) {
-  CUtensorMap mA[4], mW, mO;
+  CUtensorMap mA[4], mW, mO, mOx[3];
   for (int i = 0; i < 4; ++i) {
     const ActView& v = a[i < nmaps ? i : 0];
     int rc = make_act_map(&mA[i], v.base, v.C, v.W, v.H, v.B, v.sw, v.sh, v.sb, (ROW && i == 1) ? (int)kRowBoxPixels : p.TW, p.TH);
@@ -935,6 +948,12 @@ static int launch_fwd_impl(const ActView* a, int nmaps, const void* w, long long
   if (rc) return rc;
   rc = make_act_map(&mO, out.base, out.C, out.W, out.H, out.B, out.sw, out.sh, out.sb, p.TW, p.TH);
   if (rc) return rc;
+  for (int i = 0; i < 3; ++i) {
+    const ActView& o = (p.out_split > 0 && g_extra_outs) ? g_extra_outs[i] : out;
+    rc = (p.out_split > 0 && g_extra_outs) ? make_act_map(&mOx[i], o.base, o.C, o.W, o.H, o.B, o.sw, o.sh, o.sb, p.TW, p.TH) : 0;
+    if (rc) return rc;
+    if (!(p.out_split > 0 && g_extra_outs)) mOx[i] = mO;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     const uint32_t want = RESB ? kMaxDynSmem : smem_bytes;
@@ -942,7 +961,7 @@ static int launch_fwd_impl(const ActView* a, int nmaps, const void* w, long long
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_tc_conv<%d,%d,%d>, %u): %s", BN, (int)ROW, (int)RESB, want, cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  k_tc_conv<BN, ROW, RESB><<<p.n_tiles * p.ctas_per_n, 256, smem_bytes, st>>>(mA[0], mA[1], mA[2], mA[3], mW, mO, p);
+  k_tc_conv<BN, ROW, RESB><<<p.n_tiles * p.ctas_per_n, 256, smem_bytes, st>>>(mA[0], mA[1], mA[2], mA[3], mW, mO, mOx[0], mOx[1], mOx[2], p);
   return check_launch("k_tc_conv");
 }
 
@@ -1031,20 +1050,44 @@ int tc_conv_fwd(const void* x, int ldx, const void* w, const float* bias, void* 
   return launch_fwd<64>(&a, 1, w, Ktot, o, p, st);
 }
 
-// ConvTranspose2d(k2,s2) forward: four 1x1 GEMMs, each TMA-storing into the (2h+i, 2w+j) sub-grid
+// ConvTranspose2d(k2,s2) forward as ONE GEMM: the packed weights wf[4][Cout][Cin] are a K-major [4*Cout][Cin] matrix, so the
+// four taps are column blocks of N = 4*Cout; the input tile is read once (not four times) and every 64-channel block of the
+// epilogue is TMA-stored into its tap's (2h+i, 2w+j) sub-grid of the output (four output tensor maps).  USTRUN_TC_CONVT_FUSED=0
+// restores the four separate launches (A/B comparisons).
+static int convt_fused_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USTRUN_TC_CONVT_FUSED");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
 int tc_convT_fwd(const void* x, int ldx, const void* wf, const float* bias, void* y, int ldy, int B, int H, int W, int Cin, int Cout,
                  cudaStream_t st) {
   if (Cin % 64 || Cout % 64 || ldx % 8 || ldy % 8) { set_error("tcgen05 convT needs Cin, Cout %% 64 == 0"); return USTRUN_ERR_ARG; }
+  ActView a{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
+  ActView o[4];
+  for (int ij = 0; ij < 4; ++ij) {
+    const char* ybase = (const char*)y + ((long long)(ij >> 1) * 2 * W + (ij & 1)) * ldy * 2;
+    o[ij] = ActView{ybase, Cout, W, H, B, 2LL * ldy, 4LL * W * ldy, 4LL * H * W * ldy};
+  }
+  if (convt_fused_mode() > 0) {
+    TcConvParams p{};
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = 4 * Cout; p.ntaps = 1; p.tap_mode = TAP_NONE; p.out_split = Cout;
+    const int BN = plan_fwd_tiles(p, B, H, W, 4 * Cout);
+    p.partials = nullptr; p.bias = bias;
+    g_extra_outs = &o[1];
+    int rc = BN == 256 ? launch_fwd<256>(&a, 1, wf, Cin, o[0], p, st) : (BN == 128 ? launch_fwd<128>(&a, 1, wf, Cin, o[0], p, st) : launch_fwd<64>(&a, 1, wf, Cin, o[0], p, st));
+    g_extra_outs = nullptr;
+    return rc;
+  }
   for (int ij = 0; ij < 4; ++ij) {
     TcConvParams p{};
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ntaps = 1; p.tap_mode = TAP_NONE;
     const int BN = plan_fwd_tiles(p, B, H, W, Cout);
     p.partials = nullptr; p.bias = bias;
-    ActView a{x, Cin, W, H, B, ldx, (long long)W * ldx, (long long)H * W * ldx};
-    const char* ybase = (const char*)y + ((long long)(ij >> 1) * 2 * W + (ij & 1)) * ldy * 2;
-    ActView o{ybase, Cout, W, H, B, 2LL * ldy, 4LL * W * ldy, 4LL * H * W * ldy};
     const char* wij = (const char*)wf + (size_t)ij * Cout * Cin * 2;
-    int rc = BN == 256 ? launch_fwd<256>(&a, 1, wij, Cin, o, p, st) : (BN == 128 ? launch_fwd<128>(&a, 1, wij, Cin, o, p, st) : launch_fwd<64>(&a, 1, wij, Cin, o, p, st));
+    int rc = BN == 256 ? launch_fwd<256>(&a, 1, wij, Cin, o[ij], p, st) : (BN == 128 ? launch_fwd<128>(&a, 1, wij, Cin, o[ij], p, st) : launch_fwd<64>(&a, 1, wij, Cin, o[ij], p, st));
     if (rc) return rc;
   }
   return 0;

@@ -30,7 +30,7 @@ LAUNCHES = 0          # C-ABI calls issued
 KERNELS = 0           # kernels those calls launched (bench.py reports it as gpu_launches)
 PROFILE_EVENTS = None  # bench.py sets this to a list: (kernel class, algorithmic FLOPs, start event, end event)
 MANIFEST = None        # tools/step_once.py sets this to a list: one dict per profiled C-ABI call, in launch order (for ncu summaries)
-_KERNELS_PER_CALL = {"ustrun_conv_wgrad": 2, "ustrun_convT2x2_wgrad": 2, "ustrun_convT2x2_fwd": 4, "ustrun_channel_sum": 2,
+_KERNELS_PER_CALL = {"ustrun_conv_wgrad": 2, "ustrun_convT2x2_wgrad": 2, "ustrun_convT2x2_fwd": 1, "ustrun_channel_sum": 2,
                      "ustrun_ce_dice_softmax_fwd": 2, "ustrun_bce_dice_sigmoid_fwd": 2}
 
 
