@@ -184,6 +184,15 @@ int ustrun_pseudo_label_sigmoid(const float* t1, const float* t2, const float* t
 int ustrun_mix_to_nhwc(const float* a, const float* b, const int* b_index, const uint8_t* box, void* dst, int ld_dst,
                        int dtype, int B, int C, int H, int W, void* stream);
 
+/* Input pipeline on the device: the reference's loaders end with Normalize_tf (custom_transforms.py:650-684:
+ * float32(u8) / 127.5 - 1.0) and ToTensor (:728-753: H x W x C -> C x H x W) on the host and copy float32 batches to the GPU
+ * (train.py:582-589).  ustrun_normalize_u8_to_nchw does both on the device, bit-exactly (uint8 [B,H,W,C] -> float32 [B,C,H,W]);
+ * ustrun_mix_any_to_nhwc is ustrun_mix_to_nhwc with either source given as such a uint8 image batch (a_u8 / b_u8, normalised on
+ * the fly) or as a float32 NCHW tensor (a_f32 / b_f32): 4x fewer bytes over PCIe, no separate normalisation pass. */
+int ustrun_normalize_u8_to_nchw(const uint8_t* src, float* dst, int B, int C, int H, int W, void* stream);
+int ustrun_mix_any_to_nhwc(const float* a_f32, const uint8_t* a_u8, const float* b_f32, const uint8_t* b_u8, const int* b_index, const uint8_t* box,
+                           void* dst, int ld_dst, int dtype, int B, int C, int H, int W, void* stream);
+
 /* ---- CE + Dice (K13,K14): train.py:816-838, utils/losses.py:194-268 ------------------------- */
 /* Pass 1 reduces (3C+1) scalars; the finalize stage (same call) writes
  *   loss_out[0] = ce_w * mean_all(CE*mask) + dice_w * DiceLossWithMask   (either weight may be 0)

@@ -671,6 +671,35 @@ def case_bank():
         torch.Tensor.cuda = saved_cuda
 
 
+def case_input():
+    """Normalize_tf + ToTensor (dataloaders/custom_transforms.py:650-684, 728-753), the two reference classes lifted with ``ast``
+    (the module itself imports matplotlib / skimage, which are absent here) and executed unmodified, vs oracle/input_ref.py."""
+    import ast
+    from oracle import input_ref as In
+    src = open(os.path.join(REF, "dataloaders", "custom_transforms.py")).read()
+    tree = ast.parse(src)
+    code = "\n\n".join(ast.get_source_segment(src, n) for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ("Normalize_tf", "ToTensor"))
+    ns = {"np": np, "torch": torch, "GetBoundary": lambda: None}
+    exec(compile(code, "custom_transforms.py", "exec"), ns)
+    rng = np.random.RandomState(SEED + 41)
+    fx = {}
+    for tag, shape in (("rgb", (4, 24, 20, 3)), ("gray", (3, 16, 16))):
+        imgs = rng.randint(0, 256, shape).astype(np.uint8)
+        imgs.reshape(-1)[:256] = np.arange(256, dtype=np.uint8)                      # every uint8 value occurs
+        out = []
+        for im in imgs:
+            sample = {"image": im, "label": np.zeros(im.shape[:2], np.uint8), "strong_aug": im[::-1].copy()}
+            sample = ns["ToTensor"]()(ns["Normalize_tf"]()(sample))
+            out.append(sample["image"])
+            assert torch.equal(sample["strong_aug"], In.normalize_to_tensor(im[::-1].copy()))
+        ref = torch.stack(out)
+        got = In.batch(imgs)
+        assert torch.equal(ref, got), f"input oracle differs ({tag})"
+        fx[tag + "/u8"], fx[tag + "/out"] = imgs, np_(ref)
+    np.savez_compressed(os.path.join(OUT, "inputs.npz"), **fx)
+    print("input: Normalize_tf + ToTensor (reference classes) == oracle on", len(fx) // 2, "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -683,6 +712,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "eval":
         case_eval()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "input":
+        case_input()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "bank":
         case_bank()
         return
@@ -693,6 +725,7 @@ def main():
     case_fft_mix()
     case_hardness()
     case_bank()
+    case_input()
     case_eval()
     case_losses()
     case_unet_a(1, 2, 32, 2)

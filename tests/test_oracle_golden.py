@@ -287,3 +287,12 @@ def test_bank_oracle_reproduces_reference_fixture():
                 lq_s, _, _, box = Bk.lq_compose(t("ulb_x_w")[[i]], pl[[i]], mask[[i]], t("lb_x_w"), lbm, nc, ds)
                 assert np.array_equal(lq_s.numpy(), fx[p + "/lq_s"]) and np.array_equal(box.numpy().astype(np.uint8), fx[p + "/lq_box"])
         assert float(fx[f"{ds}/7/choice_th_after"]) < 0.1 and int(fx[f"{ds}/2/n_bank_after"]) >= 3
+
+
+def test_input_oracle_reproduces_reference_fixture():
+    """oracle/input_ref.py against tests/golden/inputs.npz (Normalize_tf + ToTensor of the reference, executed by make_golden)."""
+    from oracle import input_ref as In
+    fx = np.load(os.path.join(GOLDEN, "inputs.npz"))
+    for tag in ("rgb", "gray"):
+        assert np.array_equal(In.batch(fx[tag + "/u8"]).numpy(), fx[tag + "/out"]), tag
+    assert float(In.normalize_to_tensor(np.full((2, 2), 255, np.uint8)).max()) == 1.0 and float(In.normalize_to_tensor(np.zeros((2, 2), np.uint8)).min()) == -1.0

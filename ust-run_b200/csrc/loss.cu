@@ -158,6 +158,39 @@ __global__ void k_mix_to_nhwc(const float* __restrict__ a, const float* __restri
   }
 }
 
+// Normalize_tf (dataloaders/custom_transforms.py:650-684): float32(u8) / 127.5 - 1.0, two separately rounded operations
+__device__ __forceinline__ float normalize_tf(uint8_t v) { return __fsub_rn(__fdiv_rn((float)v, 127.5f), 1.0f); }
+
+// Same composition with either source given as the uint8 H x W x C image the reference's loaders hold BEFORE Normalize_tf +
+// ToTensor (NHWC, normalised on the fly) or as a float32 NCHW tensor: dst[b][hw][c] = box ? B[idx[b]] : A[b]
+template <typename T>
+__global__ void k_mix_any_to_nhwc(const float* __restrict__ a_f, const uint8_t* __restrict__ a_u, const float* __restrict__ b_f, const uint8_t* __restrict__ b_u,
+                                  const int* __restrict__ b_index, const uint8_t* __restrict__ box, T* __restrict__ dst, int ld, int B, int C, int HW) {
+  const long long n = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)((unsigned int)i / (unsigned int)HW), hw = (int)((unsigned int)i - (unsigned int)b * (unsigned int)HW);
+    const bool in = box && box[i] != 0;
+    const int sb = b_index ? b_index[b] : b;
+    for (int c = 0; c < C; ++c) {
+      float v;
+      if (in) v = b_u ? normalize_tf(b_u[((size_t)sb * HW + hw) * C + c]) : b_f[((size_t)sb * C + c) * HW + hw];
+      else v = a_u ? normalize_tf(a_u[((size_t)b * HW + hw) * C + c]) : a_f[((size_t)b * C + c) * HW + hw];
+      dst[i * ld + c] = from_f<T>(v);
+    }
+  }
+}
+
+// Normalize_tf + ToTensor on the device: uint8 [B,H,W,C] -> float32 [B,C,H,W] (bit-exact with the reference's numpy ops)
+__global__ void k_normalize_u8_to_nchw(const uint8_t* __restrict__ src, float* __restrict__ dst, int B, int C, int HW) {
+  const long long n = (long long)B * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int hw = (int)(i % HW);
+    const long long bc = i / HW;
+    const int c = (int)(bc % C), b = (int)(bc / C);
+    dst[i] = normalize_tf(src[((size_t)b * HW + hw) * C + c]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // CE + Dice, softmax branch
 // ------------------------------------------------------------------------------------------
@@ -548,6 +581,29 @@ int ustrun_mix_to_nhwc(const float* a, const float* b, const int* b_index, const
   else if (dtype == USTRUN_BF16) k_mix_to_nhwc<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, b_index, box, (__nv_bfloat16*)dst, ld_dst, B, C, H * W);
   else { set_error("bad dtype"); return USTRUN_ERR_ARG; }
   return check_launch("mix_to_nhwc");
+}
+
+int ustrun_mix_any_to_nhwc(const float* a_f32, const uint8_t* a_u8, const float* b_f32, const uint8_t* b_u8, const int* b_index, const uint8_t* box,
+                           void* dst, int ld_dst, int dtype, int B, int C, int H, int W, void* stream) {
+  USTRUN_REQUIRE((a_f32 != nullptr) != (a_u8 != nullptr), "mix_any_to_nhwc: exactly one of a_f32 / a_u8");
+  USTRUN_REQUIRE(dst && B > 0 && C > 0 && ld_dst >= C && !(b_f32 && b_u8) && (!box || b_f32 || b_u8), "mix_any_to_nhwc: bad args");
+  const long long n = (long long)B * H * W;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (dtype == USTRUN_F32) k_mix_any_to_nhwc<float><<<grid, 256, 0, (cudaStream_t)stream>>>(a_f32, a_u8, b_f32, b_u8, b_index, box, (float*)dst, ld_dst, B, C, H * W);
+  else if (dtype == USTRUN_BF16)
+    k_mix_any_to_nhwc<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a_f32, a_u8, b_f32, b_u8, b_index, box, (__nv_bfloat16*)dst, ld_dst, B, C, H * W);
+  else { set_error("bad dtype"); return USTRUN_ERR_ARG; }
+  return check_launch("mix_any_to_nhwc");
+}
+
+int ustrun_normalize_u8_to_nchw(const uint8_t* src, float* dst, int B, int C, int H, int W, void* stream) {
+  USTRUN_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "normalize_u8_to_nchw: bad args");
+  const long long n = (long long)B * C * H * W;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  k_normalize_u8_to_nchw<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, B, C, H * W);
+  return check_launch("normalize_u8_to_nchw");
 }
 
 int ustrun_reduce_rows(const float* rows, int nrows, int ncols, float* out, void* stream) {

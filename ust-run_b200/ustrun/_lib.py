@@ -59,6 +59,8 @@ _SIGS = {
     "ustrun_pseudo_label_softmax": [p] * 8 + [f32, i32, i32, i32, i32] + [p] * 9 + [p],
     "ustrun_pseudo_label_sigmoid": [p] * 8 + [f32, f32, i32, i32, i32, i32] + [p] * 9 + [p],
     "ustrun_mix_to_nhwc": [p, p, p, p, p, i32, i32, i32, i32, i32, i32, p],
+    "ustrun_mix_any_to_nhwc": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, p],
+    "ustrun_normalize_u8_to_nchw": [p, p, i32, i32, i32, i32, p],
     "ustrun_ce_dice_softmax_fwd": [p, p, p, i32, i32, i32, i32, f32, f32, p, p, p, p, p],
     "ustrun_ce_dice_softmax_partials": [p, p, p, i32, i32, i32, i32, p, ip, p],
     "ustrun_ce_dice_softmax_finalize": [p, i32, i32, f64, f32, f32, p, p, p, p],

@@ -78,14 +78,45 @@ def pseudo_labels(t1, t2, t3, box, cut_label, cut_mask, choice, threshold, branc
     return res
 
 
+def normalize_u8(images_u8: torch.Tensor) -> torch.Tensor:
+    """Normalize_tf + ToTensor on the device (custom_transforms.py:650-684, 728-753): uint8 [B,H,W,C] (or [B,H,W]) -> float32
+    [B,C,H,W] in [-1, 1], bit-exact with the reference's numpy arithmetic."""
+    L.require_device()
+    x = images_u8.contiguous()
+    if x.dim() == 3:
+        x = x.unsqueeze(-1)
+    B, H, W, C = x.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    _call("ustrun_normalize_u8_to_nchw", _ptr(x), _ptr(out), B, C, H, W, _stream())
+    return out
+
+
+def _is_u8_image(t):
+    return t is not None and t.dtype == torch.uint8
+
+
 def mix_input(a, b, box_u8, b_index=None) -> E.Act:
-    """NHWC activation of ``a*(1-box) + b[b_index]*box`` (fp32 NCHW sources); box=None converts a."""
-    a = a.float().contiguous()
-    B, C, H, W = a.shape
+    """NHWC activation of ``a*(1-box) + b[b_index]*box``; box=None converts a.  Sources are float32 NCHW tensors in [-1, 1]
+    or uint8 [B,H,W,C] image batches as the loaders hold them before Normalize_tf + ToTensor (normalised on the fly)."""
+    if not (_is_u8_image(a) or _is_u8_image(b)):
+        a = a.float().contiguous()
+        B, C, H, W = a.shape
+        out = E.Act.new(B, H, W, C, device=a.device)
+        _call("ustrun_mix_to_nhwc", _ptr(a), _ptr(b.float().contiguous()) if b is not None else None,
+              _ptr(b_index) if b_index is not None else None, _ptr(box_u8) if box_u8 is not None else None, out.ptr, out.ld, out.dtype_code,
+              B, C, H, W, _stream())
+        return out
+    au = a.contiguous() if _is_u8_image(a) else None
+    af = None if au is not None else a.float().contiguous()
+    bu = b.contiguous() if _is_u8_image(b) else None
+    bf = None if (b is None or bu is not None) else b.float().contiguous()
+    if au is not None:
+        B, H, W, C = au.shape if au.dim() == 4 else (au.shape + (1,))
+    else:
+        B, C, H, W = af.shape
     out = E.Act.new(B, H, W, C, device=a.device)
-    _call("ustrun_mix_to_nhwc", _ptr(a), _ptr(b.float().contiguous()) if b is not None else None,
-          _ptr(b_index) if b_index is not None else None, _ptr(box_u8) if box_u8 is not None else None, out.ptr, out.ld, out.dtype_code,
-          B, C, H, W, _stream())
+    _call("ustrun_mix_any_to_nhwc", _ptr(af), _ptr(au), _ptr(bf), _ptr(bu), _ptr(b_index) if b_index is not None else None,
+          _ptr(box_u8) if box_u8 is not None else None, out.ptr, out.ld, out.dtype_code, B, C, H, W, _stream())
     return out
 
 
@@ -383,7 +414,9 @@ class SSLTrainer:
             # its random blend ratio per sample (train.py:180) instead of running fft2/ifft2 in numpy
             from .fft_mix import amp_mix
             b = dict(b)
-            b["move_transx"] = amp_mix(b["cut_img"].float()[choice_i.long()], b["ulb_w"], b["mix_ratio"], self.fft_window)
+            cut_f = normalize_u8(b["cut_img"]) if _is_u8_image(b["cut_img"]) else b["cut_img"].float()
+            ulb_f = normalize_u8(b["ulb_w"]) if _is_u8_image(b["ulb_w"]) else b["ulb_w"]
+            b["move_transx"] = amp_mix(cut_f[choice_i.long()], ulb_f, b["mix_ratio"], self.fft_window)
         multi = self._multi()
         if self._eager_steps > 0:
             self._pack_plan.run()                     # every packed weight copy in one launch, on this stream, before the lanes fork
