@@ -158,7 +158,9 @@ def run_ours(args):
     student, teacher = student.cuda().train(), teacher.cuda().train()
     use_graph = args.graph == "on" or (args.graph == "auto" and (dp is None or dp.graph_safe) and args.workload != "cfg5")
     # auto: the tensor-bound UNet-A gains from 2 lanes (4 thrash the L2), the latency-bound UNet-B from 4
-    lanes = args.lanes if args.lanes > 0 else (1 if (dp is not None or args.workload == "cfg5") else (2 if model_name.startswith("unet_a") else 4))
+    # data parallel: lanes need the peer-memory BatchNorm path (every cross-rank kernel on one stream)
+    dp_lanes_ok = dp is None or getattr(dp, "peer", None) is not None or not dp.sync_bn
+    lanes = args.lanes if args.lanes > 0 else (1 if (not dp_lanes_ok or args.workload == "cfg5") else (2 if model_name.startswith("unet_a") else 4))
     trainer = SSLTrainer(student, teacher, n_classes=k, branch=branch, base_lr=0.03, max_iterations=60000, threshold=0.95, dp=dp, use_graph=use_graph,
                          lanes=lanes)
     trainer.iter_num = 30000                      # mid-training: consistency weight 1.0, alpha 0.99

@@ -155,7 +155,7 @@ int ustrun_upsample2x_bwd(const void* dy, int lddy, void* dx, int lddx, int dtyp
 long long ustrun_peer_buffer_bytes(void);
 int ustrun_bn_finalize_peer(const float* partials, int nparts, int C, double count_global, const float* gamma, const float* beta,
                             const float* conv_bias, float* running_mean, float* running_var, long long* num_batches_tracked,
-                            float momentum, float eps, float* scale, float* shift, float* mean, float* rstd,
+                            float momentum, float eps, float* scale, float* shift, float* mean, float* rstd, float* stat_out,
                             const void* const* peer_bases, int rank, int world, unsigned int seq, unsigned int* counter,
                             int* error, void* stream);
 /* dgamma/dbeta receive the LOCAL sums (the gradient all-reduce adds the ranks), coef the global means */

@@ -89,3 +89,44 @@ def test_world1_data_parallel_equals_plain_step(nccl_world1, kind, sync):
     assert float((cat(s1) - cat(s0)).norm() / cat(s0).norm()) < 5e-3
     for (n, a), (_, b) in zip(s1.named_buffers(), s0.named_buffers()):
         assert float((a.double() - b.double()).norm() / (b.double().norm() + 1e-12)) < 5e-3, n
+
+
+@pytest.mark.parametrize("kind", ["a", "b_dsbn"])
+def test_world1_data_parallel_lanes_bit_identical(nccl_world1, kind):
+    """Multi-lane step under data parallelism with the peer-memory BatchNorm path: every cross-rank finalize kernel runs on the
+    ONE BN-sync stream in program order (engine.on_sync_stream), running statistics are deferred through the kernel's
+    ``stat_out`` -- the result must equal the single-lane data-parallel step bit for bit."""
+    from ustrun import bridge
+    from ustrun import engine as E
+    from ustrun import synth as S
+    from ustrun.dp import DataParallel
+    from ustrun.step import SSLTrainer
+    dsbn = kind == "b_dsbn"
+    kw = dict(norm="dsbn", num_domains=3) if dsbn else {}
+    c = 3 if dsbn else 1
+    extra = dict(domain_lb=1, domain_ulb=2) if dsbn else {}
+    batches = [{kk: v.cuda() for kk, v in S.synthetic_batch(c, 2, 64, 64, 2, 2, seed=60 + i).items()} for i in range(4)]
+    runs = []
+    for lanes in (1, 3):
+        E.set_precision("bf16")
+        s, t = _pair(kind[0], **kw)
+        try:
+            dp = DataParallel(sync_bn="peer", global_loss=True, bucket_bytes=256, force=True)
+        except Exception as e:
+            pytest.skip(f"peer-memory buffers unavailable: {type(e).__name__}: {e}")
+        try:
+            tr = SSLTrainer(s, t, n_classes=2, threshold=0.6, dp=dp, lanes=lanes)
+            assert tr.lanes == lanes
+            losses = [tr.step({**b, **extra}, lq=b["ulb_w"][:1].contiguous())["loss"].clone() for b in batches]
+            torch.cuda.synchronize()
+            dp.peer.check()
+        finally:
+            dp.close()
+            assert bridge.BN_SYNC is None
+        runs.append((losses, s, t))
+    (l1, s1, t1), (l3, s3, t3) = runs
+    for a, b in zip(l1, l3):
+        assert float(a) == float(b)
+    for m1, m3 in ((s1, s3), (t1, t3)):
+        for (n, a), (_, b) in zip(list(m1.named_parameters()) + list(m1.named_buffers()), list(m3.named_parameters()) + list(m3.named_buffers())):
+            assert torch.equal(a, b), n

@@ -42,12 +42,29 @@ def main():
     local_batch = {kk: (v[sl] if kk in ("lb_x", "lb_mask", "ulb_w", "ulb_s", "move_transx", "box", "choice") else v) for kk, v in full.items()}
     dp = DataParallel(sync_bn=os.environ.get("USTRUN_SYNC_BN", "peer"), global_loss=True, bucket_bytes=8 << 20)
     s_dp, t_dp = models()
-    tr = SSLTrainer(s_dp, t_dp, n_classes=k, threshold=0.6, dp=dp)
+    lanes = int(os.environ.get("USTRUN_DP_LANES", "1"))
+    tr = SSLTrainer(s_dp, t_dp, n_classes=k, threshold=0.6, dp=dp, lanes=lanes)
     tr.iter_num = 3000
     outs = [tr.step({**{kk: v.cuda() for kk, v in local_batch.items()}, **extra}) for _ in range(2)]
     torch.cuda.synchronize()
     if dp.peer is not None:
         dp.peer.check()
+    if lanes > 1:
+        # multi-lane data-parallel step (the first step of a trainer is single-lane, the second one above ran on the lanes) == single-lane data-parallel step, bit for bit
+        s_l1, t_l1 = models()
+        tr_l1 = SSLTrainer(s_l1, t_l1, n_classes=k, threshold=0.6, dp=dp, lanes=1)
+        tr_l1.iter_num = 3000
+        for _ in range(2):
+            tr_l1.step({**{kk: v.cuda() for kk, v in local_batch.items()}, **extra})
+        torch.cuda.synchronize()
+        dp.peer.check()
+        bit = all(torch.equal(a, b) for a, b in zip(list(s_dp.parameters()) + list(s_dp.buffers()) + list(t_dp.parameters()) + list(t_dp.buffers()),
+                                                     list(s_l1.parameters()) + list(s_l1.buffers()) + list(t_l1.parameters()) + list(t_l1.buffers())))
+        flags = [torch.zeros(1, device="cuda") for _ in range(world)]
+        dist.all_gather(flags, torch.tensor([float(bit)], device="cuda"))
+        if rank == 0:
+            print(f"dp_check lanes={tr.lanes}: multi-lane == single-lane data-parallel step, bit-identical on every rank: {[bool(f.item()) for f in flags]}")
+        assert bit, "multi-lane data-parallel step differs from the single-lane one"
     if rank == 0:
         print("BN statistics path:", "peer-memory fused finalize" if dp.peer is not None else "NCCL all-reduce")
     dp.close()

@@ -86,7 +86,7 @@ __device__ __forceinline__ void peer_allreduce2(const PeerCtx& p, int c, int lan
 __global__ void k_bn_finalize_peer(const float* __restrict__ partials, int nparts, int C, double count_global,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ conv_bias,
                                    float* running_mean, float* running_var, long long* nbt, float momentum, float eps, float* scale,
-                                   float* shift, float* mean_out, float* rstd_out, PeerCtx p) {
+                                   float* shift, float* mean_out, float* rstd_out, float* stat_out, PeerCtx p) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
   if (c >= C) return;
@@ -111,10 +111,16 @@ __global__ void k_bn_finalize_peer(const float* __restrict__ partials, int npart
   shift[c] = b - mf * g * rstd;
   mean_out[c] = mf;
   rstd_out[c] = rstd;
-  if (running_mean) {
+  if (running_mean || stat_out) {
     const double unbiased = count_global > 1.0 ? var * count_global / (count_global - 1.0) : var;
-    running_mean[c] = bn_running(running_mean[c], __fadd_rn(mf, cb), momentum);
-    running_var[c] = bn_running(running_var[c], (float)unbiased, momentum);
+    const float bm = __fadd_rn(mf, cb), bv = (float)unbiased;
+    if (stat_out) {              // deferred (multi-lane step): ustrun_bn_running_update applies the forwards in the reference's order
+      stat_out[c] = bm;
+      stat_out[C + c] = bv;
+    } else {
+      running_mean[c] = bn_running(running_mean[c], bm, momentum);
+      running_var[c] = bn_running(running_var[c], bv, momentum);
+    }
   }
 }
 
@@ -177,14 +183,15 @@ long long ustrun_peer_buffer_bytes(void) { return 2LL * PEER_MAXW * PEER_CMAX * 
 
 int ustrun_bn_finalize_peer(const float* partials, int nparts, int C, double count_global, const float* gamma, const float* beta,
                             const float* conv_bias, float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
-                            float* scale, float* shift, float* mean, float* rstd, const void* const* peer_bases, int rank, int world,
+                            float* scale, float* shift, float* mean, float* rstd, float* stat_out, const void* const* peer_bases, int rank, int world,
                             unsigned int seq, unsigned int* counter, int* error, void* stream) {
   USTRUN_REQUIRE(partials && nparts > 0 && C > 0 && C <= PEER_CMAX && count_global > 0 && scale && shift && mean && rstd, "bn_finalize_peer: bad args");
+  USTRUN_REQUIRE(!stat_out || (!running_mean && !running_var && !nbt), "bn_finalize_peer: stat_out replaces the in-place running update");
   PeerCtx p;
   int rc = fill_ctx(p, peer_bases, rank, world, seq, counter, error);
   if (rc) return rc;
   k_bn_finalize_peer<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nparts, C, count_global, gamma, beta, conv_bias, running_mean, running_var,
-                                                                      nbt, momentum, eps, scale, shift, mean, rstd, p);
+                                                                      nbt, momentum, eps, scale, shift, mean, rstd, stat_out, p);
   return check_launch("bn_finalize_peer");
 }
 

@@ -70,7 +70,7 @@ _SIGS = {
     "ustrun_ce_dice_softmax_bwd": [p, p, p, i32, i32, i32, i32, p, p, f32, p, i32, p],
     "ustrun_bce_dice_sigmoid_fwd": [p, p, p, i32, i32, i32, i32, f32, f32, p, p, p, p],
     "ustrun_bce_dice_sigmoid_bwd": [p, p, p, i32, i32, i32, i32, p, p, f32, p, i32, p],
-    "ustrun_bn_finalize_peer": [p, i32, i32, f64, p, p, p, p, p, p, f32, f32, p, p, p, p, p, i32, i32, C.c_uint, p, p, p],
+    "ustrun_bn_finalize_peer": [p, i32, i32, f64, p, p, p, p, p, p, f32, f32, p, p, p, p, p, p, i32, i32, C.c_uint, p, p, p],
     "ustrun_bn_bwd_finalize_peer": [p, i32, i32, f64, p, p, p, p, i32, p, p, i32, i32, C.c_uint, p, p, p],
     "ustrun_sgd_ema_multi": [p, p, p, i32, f32, f32, f32, f32, f32, i32, i32, p],
     "ustrun_sgd_ema_multi_dev": [p, p, p, i32, p, f32, f32, i32, i32, p],

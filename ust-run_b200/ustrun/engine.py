@@ -135,6 +135,29 @@ def _side_stream():
     return st
 
 
+_SYNC: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def on_sync_stream(fn: Callable) -> None:
+    """Run ``fn`` (a cross-rank BatchNorm finalize kernel that WAITS for the other ranks) on the one BN-sync stream, ordered
+    after the current stream's work, and make the current stream wait for it.  In the multi-lane data-parallel step every
+    such kernel of every lane goes through this stream in program order, so all ranks execute them in the same order whatever
+    the lanes do -- two ranks can never wait for each other's kernels in crossed order."""
+    dev = torch.cuda.current_device()
+    st = _SYNC.get(dev)
+    if st is None:
+        st = _SYNC[dev] = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    with torch.cuda.stream(st):
+        st.wait_event(ev)
+        fn()
+        done = torch.cuda.Event()
+        done.record(st)
+    cur.wait_event(done)
+
+
 _HELD: List = []          # operands of side-stream kernels enqueued during a CUDA-graph capture (see on_side_stream)
 _SIDE_DIRTY = [False]     # the side stream has work the current stream has not joined yet
 
@@ -559,17 +582,24 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
     count = float(x.npix)
     track = bn.track_running_stats and bn.running_mean is not None and training
     peer = ctx.bn_peer if use_batch_stats else None
-    stat_ptr = ctx.stats.slot_ptr(bn, ctx.slot) if (track and ctx.stats is not None and ctx.bn_sync is None) else None
+    stat_ptr = ctx.stats.slot_ptr(bn, ctx.slot) if (track and ctx.stats is not None and (ctx.bn_sync is None or peer is not None)) else None
     if use_batch_stats and ctx.bn_sync is not None and peer is None:
         sums = torch.empty(2 * cout, dtype=torch.float32, device=dev)
         _call("ustrun_bn_reduce_partials", _ptr(partials), nparts, cout, _ptr(sums), _stream())
         ctx.bn_sync(sums)
         partials, nparts, count = sums, 1, count * ctx.bn_world
     if peer is not None:
-        _call("ustrun_bn_finalize_peer", _ptr(partials), nparts, cout, count * ctx.bn_world, _ptr(bn.weight), _ptr(bn.bias), _ptr(conv.bias),
-              _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
-              _ptr(bn.num_batches_tracked) if track else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
-              _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), *peer.args(), _stream())
+        inpl = track and stat_ptr is None
+        pargs = peer.args()                    # sequence number taken in PROGRAM order
+        def fin_fn():
+            _call("ustrun_bn_finalize_peer", _ptr(partials), nparts, cout, count * ctx.bn_world, _ptr(bn.weight), _ptr(bn.bias), _ptr(conv.bias),
+                  _ptr(bn.running_mean) if inpl else None, _ptr(bn.running_var) if inpl else None,
+                  _ptr(bn.num_batches_tracked) if inpl else None, 0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps),
+                  _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), stat_ptr, *pargs, _stream())
+        if ctx.grads_on_side:
+            on_sync_stream(fin_fn)
+        else:
+            fin_fn()
     else:
       inplace = (track and stat_ptr is None) or not use_batch_stats
       _call("ustrun_bn_finalize", _ptr(partials), nparts, cout, count, _ptr(bn.weight), _ptr(bn.bias), _ptr(conv.bias),
@@ -588,6 +618,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
         bn_sync = ctx.bn_sync
         bn_peer = ctx.bn_peer
         gos = ctx.grads_on_side and bn_sync is None
+        multi_lane = ctx.grads_on_side
 
         def bwd(sink: GradSink):
             G = y.g
@@ -607,8 +638,15 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
             dg, acc_g = sink.get(bn.weight) if bn.weight is not None else (None, 0)
             db, acc_b = sink.get(bn.bias) if bn.bias is not None else (None, 0)
             if bn_peer is not None:
-                _call("ustrun_bn_bwd_finalize_peer", _ptr(part), n_parts, cout, cnt * world, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
-                      1 if (acc_g or acc_b) else 0, _ptr(coef), *bn_peer.args(), _stream())
+                pargs = bn_peer.args()
+                def bfin_fn(part=part, n_parts=n_parts, cnt=cnt):
+                    _call("ustrun_bn_bwd_finalize_peer", _ptr(part), n_parts, cout, cnt * world, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
+                          1 if (acc_g or acc_b) else 0, _ptr(coef), *pargs, _stream())
+                    sink.done(bn.weight, bn.bias)
+                if multi_lane:
+                    on_sync_stream(bfin_fn)      # dgamma / dbeta of all lanes accumulate on this one stream, in program order
+                else:
+                    bfin_fn()
             elif bn_sync is not None:
                 sums = torch.empty(2 * cout, dtype=torch.float32, device=dev)
                 _call("ustrun_bn_reduce_partials", _ptr(part), n_parts, cout, _ptr(sums), _stream())
@@ -625,7 +663,7 @@ def conv_bn_act(ctx: Ctx, x: Act, conv, bn, act: int, out: Optional[Act] = None,
             elif bn_peer is None:
               _call("ustrun_bn_bwd_finalize", _ptr(part), n_parts, cout, cnt, _ptr(bn.weight), _ptr(rstd), _ptr(dg), _ptr(db),
                   1 if (acc_g or acc_b) else 0, 1.0 / world if bn_sync is not None else 1.0, _ptr(coef), _stream())
-            if not (bn_peer is None and gos):
+            if bn_peer is None and not gos:
                 sink.done(bn.weight, bn.bias)
             draw = raw.like()
             _profiled("hbm_bn_bwd_apply", raw.npix * cout * raw.t.element_size() * 3.0, "ustrun_bn_bwd_apply", G.ptr, G.ld, raw.ptr, raw.ld, _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(coef),
@@ -673,7 +711,7 @@ def conv_transpose2x2(ctx: Ctx, x: Act, up, out: Act, packed: PackedConv):
               meta=(x.B, x.H, x.W, cin, cout, "T"))
     if ctx.need_grad:
         dev = x.t.device
-        gos = ctx.grads_on_side and ctx.bn_sync is None
+        gos = ctx.grads_on_side
 
         def bwd(sink: GradSink):
             G = out.g
@@ -734,7 +772,7 @@ def head_conv(ctx: Ctx, x: Act, conv, packed: PackedConv):
     wf, wd = packed.get(conv.weight, need_wd=ctx.need_grad or conv.weight.requires_grad)
     logits = torch.empty((x.B, cout, x.H, x.W), dtype=torch.float32, device=x.t.device)
     _raw_conv(x, wf, conv.bias, None, ks, out_nchw=logits)
-    gos = ctx.grads_on_side and ctx.bn_sync is None
+    gos = ctx.grads_on_side
 
     def bwd(dlogits: torch.Tensor, sink: GradSink):
         dev = x.t.device

@@ -173,7 +173,10 @@ class SSLTrainer:
         # are logged per forward and applied in the reference's order at the end of the step (E.StatLog), and every
         # parameter-gradient accumulation runs on the one weight-gradient stream in program order.  Single GPU only (the
         # peer-memory BatchNorm kernels of the data-parallel step wait on other ranks and must not be reordered).
-        self.lanes = max(1, int(lanes)) if dp is None else 1
+        # Data parallel: lanes are allowed with the peer-memory BatchNorm path (every cross-rank kernel then runs on ONE
+        # stream in program order, engine.on_sync_stream) and without cross-rank statistics; not with per-layer NCCL calls.
+        dp_ok = dp is None or not getattr(dp, "active", False) or not dp.sync_bn or getattr(dp, "peer", None) is not None
+        self.lanes = max(1, int(lanes)) if dp_ok else 1
         self._lane_streams = []
         self._stats = E.StatLog() if self.lanes > 1 else None
         self._pack_plan = E.PackPlan(E.collect_packed(model, ema_model))
