@@ -151,6 +151,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from ustrun.dp import DataParallel
         dp = DataParallel(sync_bn=False if args.no_sync_bn else (args.sync_bn if args.sync_bn != "auto" else True))
+    elif os.environ.get("USTRUN_BENCH_FORCE_DP"):
+        # debugging aid: the complete data-parallel code path (buckets, peer-memory BatchNorm kernels, global loss sums) on ONE GPU
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
+        from ustrun.dp import DataParallel
+        dp = DataParallel(sync_bn="peer", force=True)
     model_name, c, k, H, W, Bl, Bu, branch = WORKLOADS[args.workload]
     dsbn = model_name.endswith("_dsbn3")
     E.set_precision(args.precision)
@@ -233,6 +240,8 @@ def run_ours(args):
     parity_pl0 = out0["pseudo_label"].detach().clone()
     for _ in range(max(args.warmup, 3 if use_graph else 0) - 1):
         step_resident()
+    if use_graph and not trainer.use_graph:      # data parallel: the capture (NCCL calls included) failed and the trainer fell back to eager steps
+        use_graph = False
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -320,7 +329,7 @@ def run_ours(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"{args.workload}: {model_name} {c}x{H}x{W}, {k} classes, {Bl}+{Bu} per GPU, {branch} branch, SSL step",
                        "global_batch": imgs, "parallelism": f"dp{world}", "l2": "working set (GBs of activations per step) >> 126 MB L2; no flush needed", "pool_reserved_gib": round(pool / 2**30, 1),
-                       "cuda_graph": bool(use_graph), "lanes": trainer.lanes, "dsbn_domains": list(DSBN_DOMAINS) if dsbn else None,
+                       "cuda_graph": bool(use_graph), "graph_error": getattr(trainer, "graph_error", None), "lanes": trainer.lanes, "dsbn_domains": list(DSBN_DOMAINS) if dsbn else None,
                        "sync_bn": (False if (world == 1 or args.no_sync_bn) else ("peer" if dp is not None and dp.peer is not None else "nccl"))},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "clocks": sampler_e2e.summary(),
                     "how": "trainer.upload(pinned host batch) + trainer.step(), software-pipelined: every timed step uploads one batch (the next step's, on a copy stream, overlapping this step's kernels) and reads one loss on the host (the previous step's: the host blocks on that D2H copy's event, not on the whole stream)"},

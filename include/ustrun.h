@@ -149,19 +149,24 @@ int ustrun_upsample2x_bwd(const void* dy, int lddy, void* dx, int lddx, int dtyp
 /* ---- BatchNorm finalize fused with the cross-rank reduction over NVLink peer memory ----
  * peer_bases: HOST array of `world` device pointers, entry r = rank r's symmetric buffer of
  * ustrun_peer_buffer_bytes() bytes (zero-initialised once, e.g. torch.distributed._symmetric_memory),
- * mapped into this process.  `seq` must be the same, strictly increasing number on every rank for
- * each call; counter (uint32, zeroed once) and error (int32) are local device scalars.  One kernel
- * replaces {partial-row reduction, NCCL all-reduce of 2*C floats, finalize}. */
+ * mapped into this process.  The barrier's sequence number is (seq - 1 + *seq_base) % 0x7FFFFFFE + 1 and must be the
+ * same on every rank and consecutive from call to call: `seq` (launch argument, >= 1) is the call's index within the
+ * step, `seq_base` a local device word (uint32, nullable = 0) that the host advances once per step by the number of
+ * calls of the step before -- the launch arguments then repeat from step to step and a captured CUDA graph of the
+ * data-parallel step can be replayed.  error (int32) is a local device scalar, set to 1 when a peer did not answer
+ * within ~10 s.  stat_out (nullable, excludes running_* / num_batches_tracked): [2*C] = {batch mean + conv bias,
+ * unbiased variance} for a deferred ustrun_bn_running_update.  One kernel replaces {partial-row reduction, NCCL
+ * all-reduce of 2*C floats, finalize}. */
 long long ustrun_peer_buffer_bytes(void);
 int ustrun_bn_finalize_peer(const float* partials, int nparts, int C, double count_global, const float* gamma, const float* beta,
                             const float* conv_bias, float* running_mean, float* running_var, long long* num_batches_tracked,
                             float momentum, float eps, float* scale, float* shift, float* mean, float* rstd, float* stat_out,
-                            const void* const* peer_bases, int rank, int world, unsigned int seq, unsigned int* counter,
+                            const void* const* peer_bases, int rank, int world, unsigned int seq, unsigned int* seq_base,
                             int* error, void* stream);
 /* dgamma/dbeta receive the LOCAL sums (the gradient all-reduce adds the ranks), coef the global means */
 int ustrun_bn_bwd_finalize_peer(const float* partials, int nparts, int C, double count_global, const float* gamma,
                                 const float* rstd, float* dgamma, float* dbeta, int accumulate, float* coef,
-                                const void* const* peer_bases, int rank, int world, unsigned int seq, unsigned int* counter,
+                                const void* const* peer_bases, int rank, int world, unsigned int seq, unsigned int* seq_base,
                                 int* error, void* stream);
 
 /* ---- pseudo labels (K12): train.py:649-697, train_mnms.py:595-623 -------------------------- */

@@ -95,7 +95,8 @@ def test_world1_data_parallel_equals_plain_step(nccl_world1, kind, sync):
 def test_world1_data_parallel_lanes_bit_identical(nccl_world1, kind):
     """Multi-lane step under data parallelism with the peer-memory BatchNorm path: every cross-rank finalize kernel runs on the
     ONE BN-sync stream in program order (engine.on_sync_stream), running statistics are deferred through the kernel's
-    ``stat_out`` -- the result must equal the single-lane data-parallel step bit for bit."""
+    ``stat_out`` -- the result must equal the single-lane data-parallel step bit for bit.  So must the CUDA-graph replay of the
+    data-parallel step (sequence numbers of the barriers from the device-side base, include/ustrun.h)."""
     from ustrun import bridge
     from ustrun import engine as E
     from ustrun import synth as S
@@ -105,9 +106,9 @@ def test_world1_data_parallel_lanes_bit_identical(nccl_world1, kind):
     kw = dict(norm="dsbn", num_domains=3) if dsbn else {}
     c = 3 if dsbn else 1
     extra = dict(domain_lb=1, domain_ulb=2) if dsbn else {}
-    batches = [{kk: v.cuda() for kk, v in S.synthetic_batch(c, 2, 64, 64, 2, 2, seed=60 + i).items()} for i in range(4)]
+    batches = [{kk: v.cuda() for kk, v in S.synthetic_batch(c, 2, 64, 64, 2, 2, seed=60 + i).items()} for i in range(6)]
     runs = []
-    for lanes in (1, 3):
+    for lanes, graph in ((1, False), (3, False), (2, True)):
         E.set_precision("bf16")
         s, t = _pair(kind[0], **kw)
         try:
@@ -115,18 +116,24 @@ def test_world1_data_parallel_lanes_bit_identical(nccl_world1, kind):
         except Exception as e:
             pytest.skip(f"peer-memory buffers unavailable: {type(e).__name__}: {e}")
         try:
-            tr = SSLTrainer(s, t, n_classes=2, threshold=0.6, dp=dp, lanes=lanes)
+            assert dp.graph_safe
+            tr = SSLTrainer(s, t, n_classes=2, threshold=0.6, dp=dp, lanes=lanes, use_graph=graph)
             assert tr.lanes == lanes
             losses = [tr.step({**b, **extra}, lq=b["ulb_w"][:1].contiguous())["loss"].clone() for b in batches]
             torch.cuda.synchronize()
             dp.peer.check()
+            if graph:       # steps 3.. were replays of ONE captured graph (NCCL bucket / loss-sum all-reduces and peer-BN kernels inside)
+                assert tr.use_graph and len(tr._graphs) == 1, getattr(tr, "graph_error", None)
+            assert dp.peer.seq == runs[0][3] if runs else True        # same number of cross-rank barriers whichever way the step ran
+            nseq = dp.peer.seq
         finally:
             dp.close()
             assert bridge.BN_SYNC is None
-        runs.append((losses, s, t))
-    (l1, s1, t1), (l3, s3, t3) = runs
-    for a, b in zip(l1, l3):
-        assert float(a) == float(b)
-    for m1, m3 in ((s1, s3), (t1, t3)):
-        for (n, a), (_, b) in zip(list(m1.named_parameters()) + list(m1.named_buffers()), list(m3.named_parameters()) + list(m3.named_buffers())):
-            assert torch.equal(a, b), n
+        runs.append((losses, s, t, nseq))
+    l1, s1, t1, _ = runs[0]
+    for lx, sx, tx, _ in runs[1:]:
+        for a, b in zip(l1, lx):
+            assert float(a) == float(b)
+        for m1, mx in ((s1, sx), (t1, tx)):
+            for (n, a), (_, b) in zip(list(m1.named_parameters()) + list(m1.named_buffers()), list(mx.named_parameters()) + list(mx.named_buffers())):
+                assert torch.equal(a, b), n

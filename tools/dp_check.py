@@ -43,28 +43,34 @@ def main():
     dp = DataParallel(sync_bn=os.environ.get("USTRUN_SYNC_BN", "peer"), global_loss=True, bucket_bytes=8 << 20)
     s_dp, t_dp = models()
     lanes = int(os.environ.get("USTRUN_DP_LANES", "1"))
-    tr = SSLTrainer(s_dp, t_dp, n_classes=k, threshold=0.6, dp=dp, lanes=lanes)
+    graph = os.environ.get("USTRUN_DP_USE_GRAPH", "0") == "1"
+    tr = SSLTrainer(s_dp, t_dp, n_classes=k, threshold=0.6, dp=dp, lanes=lanes, use_graph=graph)
     tr.iter_num = 3000
     outs = [tr.step({**{kk: v.cuda() for kk, v in local_batch.items()}, **extra}) for _ in range(2)]
     torch.cuda.synchronize()
     if dp.peer is not None:
         dp.peer.check()
-    if lanes > 1:
-        # multi-lane data-parallel step (the first step of a trainer is single-lane, the second one above ran on the lanes) == single-lane data-parallel step, bit for bit
-        s_l1, t_l1 = models()
-        tr_l1 = SSLTrainer(s_l1, t_l1, n_classes=k, threshold=0.6, dp=dp, lanes=1)
-        tr_l1.iter_num = 3000
-        for _ in range(2):
-            tr_l1.step({**{kk: v.cuda() for kk, v in local_batch.items()}, **extra})
-        torch.cuda.synchronize()
-        dp.peer.check()
-        bit = all(torch.equal(a, b) for a, b in zip(list(s_dp.parameters()) + list(s_dp.buffers()) + list(t_dp.parameters()) + list(t_dp.buffers()),
-                                                     list(s_l1.parameters()) + list(s_l1.buffers()) + list(t_l1.parameters()) + list(t_l1.buffers())))
+    if lanes > 1 or graph:
+        # multi-lane (and, with USTRUN_DP_USE_GRAPH=1, CUDA-graph replayed: steps 3-5) data-parallel step == single-lane eager
+        # data-parallel step, bit for bit, on fresh model pairs
+        finals = []
+        for ln, gr in ((lanes, graph), (1, False)):
+            s_x, t_x = models()
+            tr_x = SSLTrainer(s_x, t_x, n_classes=k, threshold=0.6, dp=dp, lanes=ln, use_graph=gr)
+            tr_x.iter_num = 3000
+            for _ in range(5):
+                tr_x.step({**{kk: v.cuda() for kk, v in local_batch.items()}, **extra})
+            torch.cuda.synchronize()
+            dp.peer.check()
+            if gr:
+                assert tr_x.use_graph and len(tr_x._graphs) == 1, getattr(tr_x, "graph_error", None)
+            finals.append([q.detach().clone() for q in list(s_x.parameters()) + list(s_x.buffers()) + list(t_x.parameters()) + list(t_x.buffers())])
+        bit = all(torch.equal(a, b) for a, b in zip(*finals))
         flags = [torch.zeros(1, device="cuda") for _ in range(world)]
         dist.all_gather(flags, torch.tensor([float(bit)], device="cuda"))
         if rank == 0:
-            print(f"dp_check lanes={tr.lanes}: multi-lane == single-lane data-parallel step, bit-identical on every rank: {[bool(f.item()) for f in flags]}")
-        assert bit, "multi-lane data-parallel step differs from the single-lane one"
+            print(f"dp_check lanes={lanes} graph={graph}: == single-lane eager data-parallel step after 5 steps, bit-identical on every rank: {[bool(f.item()) for f in flags]}")
+        assert bit, "multi-lane / graph-replayed data-parallel step differs from the single-lane eager one"
     if rank == 0:
         print("BN statistics path:", "peer-memory fused finalize" if dp.peer is not None else "NCCL all-reduce")
     dp.close()

@@ -17,6 +17,8 @@
 // (parts: low/high word of the first double, low/high word of the second).  Two slots (sequence parity) are
 // enough: a rank can run at most one barrier ahead of any peer, because finishing barrier k needs every
 // peer's packets of barrier k, which a peer pushes only after it has finished reading barrier k-1.
+// Sequence numbers: `seq` (launch argument) + `*seq_base` (device word the host advances once per step), so the launch
+// arguments of a step never change and the whole data-parallel step can be replayed as a CUDA graph.
 #include "common.cuh"
 
 namespace ustrun {
@@ -28,8 +30,9 @@ constexpr long long PEER_TIMEOUT_CYCLES = 20000000000LL;    // ~10 s: never hang
 struct PeerCtx {
   unsigned char* base[PEER_MAXW];   // peer-mapped base address of every rank's buffer (own included)
   int rank, world;
-  unsigned int seq;                 // same non-zero value on every rank for this call
-  unsigned int* counter;            // unused (kept in the ABI)
+  unsigned int seq;                 // same non-zero value on every rank for this call (with seq_base: its 1-based index within the step)
+  const unsigned int* seq_base;     // device word (or null): barriers completed in earlier steps, modulo 0x7FFFFFFE; lets the launch
+                                    // arguments stay the same from step to step, so a captured CUDA graph of the step can be replayed
   int* error;                       // local: set to 1 on timeout
 };
 
@@ -49,7 +52,8 @@ __device__ __forceinline__ uint2 ld_packet(const uint2* src) {
 // rank l / 4, part l % 4: world <= 8 ranks x 4 packets = one packet per lane each way.  Returns the sums over all ranks
 // (in every lane); on a timeout sets *error and leaves the local sums.
 __device__ __forceinline__ void peer_allreduce2(const PeerCtx& p, int c, int lane, double& a, double& b) {
-  const unsigned int seq = p.seq;
+  // effective sequence number 1 .. 2^31-2: consecutive over consecutive barriers (the modulus is even: slot parity alternates)
+  const unsigned int seq = p.seq_base ? (p.seq - 1u + *p.seq_base) % 0x7FFFFFFEu + 1u : p.seq;
   const int slot = (int)(seq & 1u);
   const int r = lane >> 2, part = lane & 3;
   const bool active = r < p.world;
@@ -169,7 +173,7 @@ static int fill_ctx(PeerCtx& p, const void* const* peer_bases, int rank, int wor
     return USTRUN_ERR_ARG;
   }
   for (int r = 0; r < PEER_MAXW; ++r) p.base[r] = (unsigned char*)(r < world ? peer_bases[r] : nullptr);
-  p.rank = rank; p.world = world; p.seq = seq; p.counter = counter; p.error = error;
+  p.rank = rank; p.world = world; p.seq = seq; p.seq_base = counter; p.error = error;
   return 0;
 }
 

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -108,21 +110,50 @@ class PeerStats:
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, grp)
         self._bases = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
-        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        # sequence numbers: barriers of completed steps (host `total`, device word `base` = total mod 0x7FFFFFFE, advanced by
+        # begin_step) + the call's index within the step (launch argument): see include/ustrun.h
+        self.base = torch.zeros(1, dtype=torch.int32, device=dev)
         self.error = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.seq = 0
+        self.total = 0
+        self.calls = 0
+        self._ring = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(4)]
+        self._ring_ev = [None] * 4
+        self._ring_i = 0
         self._ctypes = ctypes
         self._poll_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._poll_ev = None
         torch.cuda.synchronize()
         dist.barrier(grp)
 
+    SEQ_MOD = 0x7FFFFFFE
+
+    @property
+    def seq(self):
+        """Barriers issued so far."""
+        return self.total + self.calls
+
+    def begin_step(self):
+        """Once per step, on the stream the step is about to run on and OUTSIDE any graph capture: fold the previous step's
+        calls into the device-side base.  The launch arguments of the step's finalize kernels (1, 2, 3, ...) then repeat from
+        step to step -- what a CUDA-graph replay needs."""
+        self.total += self.calls
+        self.calls = 0
+        i = self._ring_i & 3
+        self._ring_i += 1
+        if self._ring_ev[i] is not None:
+            self._ring_ev[i].synchronize()            # the copy that last read this pinned word (four steps ago) is done
+        self._ring[i][0] = self.total % self.SEQ_MOD
+        self.base.copy_(self._ring[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ring_ev[i] = ev
+
     def args(self):
-        """(peer_bases, rank, world, seq, counter, error) for ustrun_bn_*_finalize_peer; every rank
+        """(peer_bases, rank, world, seq, seq_base, error) for ustrun_bn_*_finalize_peer; every rank
         issues the same sequence of calls, so the sequence numbers agree."""
-        self.seq = self.seq % 0x7FFFFFFE + 1          # 1 .. 2^31-1: never 0 (the buffers start zeroed)
+        self.calls += 1
         c = self._ctypes
-        return (self._bases, self.rank, self.world, self.seq, c.c_void_p(self.counter.data_ptr()), c.c_void_p(self.error.data_ptr()))
+        return (self._bases, self.rank, self.world, self.calls, c.c_void_p(self.base.data_ptr()), c.c_void_p(self.error.data_ptr()))
 
     def check(self):
         if int(self.error.item()) != 0:
@@ -174,7 +205,7 @@ class DataParallel:
         # otherwise each rank has its own loss and gradients are averaged (plain DDP semantics).
         self.global_loss = global_loss
         self.peer = None
-        self.graph_safe = False          # per-layer sequence numbers of the peer-BN kernels are launch arguments: no graph replay
+        self.graph_safe = False          # set below: replayable as a CUDA graph with the peer-memory BN path or without sync BN
         if sync_bn and self.active:
             # sync_bn="peer" (default on GPUs): finalize kernels reduce over NVLink peer memory themselves;
             # sync_bn="nccl": one NCCL all-reduce per layer and pass (validation / CPU tests)
@@ -188,6 +219,11 @@ class DataParallel:
                     print(f"[ustrun.dp] peer-memory BatchNorm statistics unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
             bridge.BN_SYNC = _BNSync(group, self.peer)
             bridge.BN_WORLD = self.world
+        # CUDA-graph replay of the whole data-parallel step: the bucket all-reduces and the loss-sum all-reduces are captured
+        # NCCL calls; the peer-memory BN kernels take their sequence number from a device word.  The per-layer NCCL BN path
+        # (validation) stays eager.
+        self.graph_safe = torch.cuda.is_available() and (self.peer is not None or not (sync_bn and self.active)) \
+            and os.environ.get("USTRUN_DP_GRAPH", "1") != "0"
 
     def close(self):
         bridge.BN_SYNC, bridge.BN_WORLD = None, 1

@@ -290,10 +290,16 @@ class SSLTrainer:
         if lq is not None:
             items["_lq_plain"] = lq
         bufs = self._staging[slot]
+        fresh = False
         for k, v in items.items():
             if isinstance(v, torch.Tensor) and (k not in bufs or bufs[k].shape != v.shape or bufs[k].dtype != v.dtype):
                 bufs[k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
+                fresh = True
         st = self._copy_stream
+        if fresh:
+            # a new staging buffer may be a block the allocator has just taken back from kernels of the CURRENT stream that are
+            # still in flight (eager steps): the copy stream must not write it before they are done
+            st.wait_stream(torch.cuda.current_stream())
         if self._consumed[slot] is not None:
             st.wait_event(self._consumed[slot])                 # the step that read this staging set has been issued and must finish first
         out = {}
@@ -337,6 +343,7 @@ class SSLTrainer:
             batch = {k: v for k, v in batch.items() if k not in ("_ustrun_ready", "_lq_plain")}
         if self.dp is not None and getattr(self.dp, "peer", None) is not None:
             self.dp.peer.poll()                     # a peer-BN timeout of an earlier step raises here (one step late, no sync)
+            self.dp.peer.begin_step()               # device-side sequence base of this step's cross-rank BN barriers
         gscale = 1.0 if self.dp is None else (1.0 if self.dp.global_loss else 1.0 / self.dp.world)
         domains = None
         if "domain_lb" in batch or "domain_ulb" in batch:
@@ -388,10 +395,27 @@ class SSLTrainer:
             torch.cuda.empty_cache()                 # the eager warm-up's cached blocks go back to the driver: the capture gets its own pool
             g = torch.cuda.CUDAGraph()
             k0 = E.KERNELS
-            with torch.cuda.graph(g):
-                out = self._step_body(static, static_lq, keep_logits, domains)
-            ent = self._graphs[key] = (g, static, static_lq, out, E.KERNELS - k0, list(self.opt.has_grad))
-        g, static, static_lq, out, self.launches_per_step, has_grad = ent
+            peer = getattr(self.dp, "peer", None) if self.dp is not None else None
+            try:
+                with torch.cuda.graph(g):
+                    out = self._step_body(static, static_lq, keep_logits, domains)
+            except Exception as e:
+                if self.dp is None:
+                    raise
+                # data parallel: the capture includes NCCL calls; if this platform cannot capture them, say so and keep stepping
+                # eagerly (an eager rank issues the same collectives in the same order as a replaying one)
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the data-parallel step failed ({type(e).__name__}: {e}); continuing without graphs")
+                self.use_graph, self.graph_error = False, f"{type(e).__name__}: {e}"
+                if peer is not None:
+                    peer.calls = 0
+                cw = self._set_hyper(it, gscale)
+                return self._step_body(tensors, lq, keep_logits, domains), cw
+            peer = getattr(self.dp, "peer", None) if self.dp is not None else None
+            ent = self._graphs[key] = (g, static, static_lq, out, E.KERNELS - k0, list(self.opt.has_grad), 0 if peer is None else peer.calls)
+        g, static, static_lq, out, self.launches_per_step, has_grad, peer_calls = ent
+        if self.dp is not None and getattr(self.dp, "peer", None) is not None:
+            self.dp.peer.calls = peer_calls          # cross-rank BN barriers this replay executes (begin_step folds them into the base)
         for i, f in enumerate(has_grad):             # host-side bookkeeping of the optimiser follows the graph that runs
             self.opt.set_has_grad(i, f)
             if f:
