@@ -134,6 +134,32 @@ def conv_flops_per_image(model, c, k, H, W):
     return f
 
 
+def shutdown_dp(trainer):
+    """End of a data-parallel run: the captured step graphs hold NCCL kernels of the communicator and have to go BEFORE it
+    (destroying the process group with such graphs alive blocks forever); then leave the process without waiting for anything
+    else -- the JSON line is out, nothing of value is left to run, and a rank that lingers stalls the launcher."""
+    import gc
+    import threading
+
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if not dist.is_initialized():
+        return
+    guard = threading.Timer(30.0, lambda: os._exit(0))      # teardown must never outlive the measurement
+    guard.daemon = True
+    guard.start()
+    torch.cuda.synchronize()
+    trainer._graphs.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+    guard.cancel()
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -273,8 +299,7 @@ def run_ours(args):
     value, e2e_value = imgs / (ms / 1e3), imgs / (ms_e2e / 1e3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown_dp(trainer)
         return
     pk = peaks()
     f_img = conv_flops_per_image(model_name, c, k, H, W)
@@ -336,8 +361,7 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "parity": parity,
             "dp_parity": dp_parity}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown_dp(trainer)
 
 
 def dp_parity_record(args, dp, rank, world):
