@@ -28,6 +28,9 @@ def nccl_world1():
     torch.cuda.set_device(0)
     dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
     yield
+    import gc
+    gc.collect()                     # step graphs that captured NCCL kernels must be gone before the communicator
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 
@@ -126,6 +129,7 @@ def test_world1_data_parallel_lanes_bit_identical(nccl_world1, kind):
                 assert tr.use_graph and len(tr._graphs) == 1, getattr(tr, "graph_error", None)
             assert dp.peer.seq == runs[0][3] if runs else True        # same number of cross-rank barriers whichever way the step ran
             nseq = dp.peer.seq
+            tr._graphs.clear()       # captured NCCL kernels: released before the process group (see bench.py::shutdown_dp)
         finally:
             dp.close()
             assert bridge.BN_SYNC is None
