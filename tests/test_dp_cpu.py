@@ -154,3 +154,29 @@ def test_dp_gradient_average_matches_single_process():
         want = (a + b) / 2
         got = flat0[offs[i]: offs[i] + a.numel()].view(a.shape)
         assert torch.allclose(got, want, rtol=1e-6, atol=1e-8)
+
+
+def test_peer_barrier_sequence_numbers():
+    """csrc/peer_bn.cu: seq_eff = (seq - 1 + *seq_base) % 0x7FFFFFFE + 1 in uint32 arithmetic, seq = index within the step
+    (launch argument, fixed under CUDA-graph replay), *seq_base = barriers of earlier steps modulo 0x7FFFFFFE (ustrun.dp.PeerStats.begin_step).
+    The protocol needs: never 0, consecutive barriers alternate parity (two packet slots), also across the wrap-around."""
+    from ustrun.dp import SEQ_MOD, barrier_seq
+
+    def device(seq, base):           # the kernel's 32-bit arithmetic
+        assert 0 <= base < SEQ_MOD and 1 <= seq < (1 << 20)
+        x = (seq - 1 + base) & 0xFFFFFFFF
+        assert x == seq - 1 + base   # no 32-bit overflow before the modulo
+        return x % SEQ_MOD + 1
+
+    per_step = 234
+    for total in (0, 1, per_step, 5 * per_step, SEQ_MOD - 300, SEQ_MOD - 1, SEQ_MOD, 3 * SEQ_MOD + 17):
+        prev = None
+        for step in range(3):
+            base = (total + step * per_step) % SEQ_MOD
+            for idx in range(1, per_step + 1):
+                s = device(idx, base)
+                assert s == barrier_seq(total + step * per_step, idx)
+                assert 1 <= s <= SEQ_MOD
+                if prev is not None:
+                    assert (s & 1) != (prev & 1) and s != prev
+                prev = s

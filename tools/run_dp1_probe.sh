@@ -1,3 +1,4 @@
+# The complete data-parallel path on ONE GPU (1-rank NCCL group): tests/test_dp_gpu.py, then bench.py with USTRUN_BENCH_FORCE_DP=1 (graph + lanes, captured NCCL calls)
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests/test_dp_gpu.py -x -q > gpurun_out/dp_test.log 2>&1; echo "rc=$?" >> gpurun_out/dp_test.log
 tail -n 25 gpurun_out/dp_test.log | cut -c1-300

@@ -1,3 +1,4 @@
+# bench.py on N GPUs of one box under torchrun, bounded by a timeout (usage: gpurun --gpus N -- bash tools/run_dpN.sh N); the JSON line lands in gpurun_out/
 N=${1:-8}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"

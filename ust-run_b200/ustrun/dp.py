@@ -92,6 +92,16 @@ class GradBuckets:
         self.works = []
 
 
+SEQ_MOD = 0x7FFFFFFE          # even: consecutive barriers alternate slot parity across the wrap-around as well
+
+
+def barrier_seq(total: int, index: int) -> int:
+    """Sequence number of the ``index``-th (1-based) cross-rank BatchNorm barrier of a step that follows ``total`` completed
+    barriers: host-side statement of what csrc/peer_bn.cu computes from its launch argument ``seq = index`` and the device word
+    ``*seq_base = total % SEQ_MOD`` in 32-bit arithmetic.  1 .. 2^31-2, never 0 (the packet buffers start zeroed)."""
+    return (total + index - 1) % SEQ_MOD + 1
+
+
 class PeerStats:
     """Symmetric (peer-mapped) buffers for the BatchNorm finalize kernels that reduce their [2*C]
     statistics across ranks themselves over NVLink (csrc/peer_bn.cu) instead of calling NCCL."""
@@ -125,7 +135,7 @@ class PeerStats:
         torch.cuda.synchronize()
         dist.barrier(grp)
 
-    SEQ_MOD = 0x7FFFFFFE
+    SEQ_MOD = SEQ_MOD
 
     @property
     def seq(self):
