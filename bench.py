@@ -550,8 +550,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-cuDNN baseline / parity leg (N=1)")
     ap.add_argument("--no-dp-parity", action="store_true", help="skip the pre-timing data-parallel parity step (N>1)")
-    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the step as one CUDA graph (auto: single GPU, not cfg5)")
-    ap.add_argument("--lanes", type=int, default=0, help="CUDA streams the independent forwards / loss branches of a step are spread over (0: auto = 4 on one GPU)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the step as one CUDA graph (auto: on, except cfg5 and data parallel with per-layer NCCL BatchNorm statistics)")
+    ap.add_argument("--lanes", type=int, default=0, help="CUDA streams the independent forwards / loss branches of a step are spread over (0: auto = 2 for UNet-A, 4 for UNet-B, 1 for cfg5)")
     ap.add_argument("--ref-budget", type=float, default=420.0, help="--impl reference: seconds of CPU time the whole run may take")
     args = ap.parse_args()
     if args.impl == "reference":

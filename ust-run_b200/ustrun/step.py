@@ -171,8 +171,7 @@ class SSLTrainer:
         # lanes > 1: the independent forwards of a step (t1 | t2 | t3 | s0, then the loss branches lb | ul | lu | s | lq) are
         # enqueued round-robin on `lanes` CUDA streams.  Results are bit-identical to lanes = 1: BatchNorm running statistics
         # are logged per forward and applied in the reference's order at the end of the step (E.StatLog), and every
-        # parameter-gradient accumulation runs on the one weight-gradient stream in program order.  Single GPU only (the
-        # peer-memory BatchNorm kernels of the data-parallel step wait on other ranks and must not be reordered).
+        # parameter-gradient accumulation runs on the one weight-gradient stream in program order.
         # Data parallel: lanes are allowed with the peer-memory BatchNorm path (every cross-rank kernel then runs on ONE
         # stream in program order, engine.on_sync_stream) and without cross-rank statistics; not with per-layer NCCL calls.
         dp_ok = dp is None or not getattr(dp, "active", False) or not dp.sync_bn or getattr(dp, "peer", None) is not None
